@@ -1,0 +1,119 @@
+/*
+ * pndf.h -- C ABI of the B200-native PoseNDF distance-field / projection engine (libpndf.so).
+ *
+ * The reference (garvita-tiwari/PoseNDF) has no plugin / FFI interface; its boundary for this path is
+ * the Python class surface of PoseNDF(nn.Module).  Every entry point below names the reference
+ * interface it replaces (file:line under the reference root).  All signatures are plain C: pointers,
+ * sizes, ints.  No torch types, no exceptions across the ABI.
+ *
+ * Conventions
+ *   - return value: 0 = ok, non-zero = error (message via pndf_last_error(), thread-local).
+ *   - "dev" pointers are CUDA device pointers on the handle's device, contiguous fp32, 16-byte aligned.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all device work is enqueued
+ *     on it, nothing synchronises implicitly, the caller owns every buffer it passes in.
+ *   - the library owns only what hangs off the handle (packed weight stream, per-CTA scratch).
+ *   - a pose is 21 joints x 4 quaternion components, row-major, 84 floats = 336 bytes.
+ *   - a handle is not thread-safe; use one handle per device per thread.
+ */
+#ifndef PNDF_H_
+#define PNDF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNDF_ACT_RELU 0     /* nn.ReLU                       model/network/net_modules.py:34-36,86-92  */
+#define PNDF_ACT_LRELU 1    /* nn.LeakyReLU() slope 0.01     model/network/net_modules.py:30-32,94-100 */
+#define PNDF_ACT_SOFTPLUS 2 /* nn.Softplus(beta), thr 20     model/network/net_modules.py:39-41,101-107 */
+
+#define PNDF_NUM_JOINTS 21
+#define PNDF_POSE_FLOATS 84
+#define PNDF_MAX_HIDDEN 8
+
+/* The slice of the reference's `opt` dict the hot path reads (model/posendf.py:35-55,
+ * model/network/net_modules.py:14-15,30-41,128). */
+typedef struct pndf_config {
+    int32_t use_enc;               /* opt['model']['StrEnc']['use']                                    */
+    int32_t enc_act;               /* opt['model']['StrEnc']['act']   -> PNDF_ACT_*                    */
+    float enc_beta;                /* opt['model']['StrEnc']['beta']                                   */
+    int32_t df_act;                /* opt['model']['DFNet']['act']                                     */
+    float df_beta;                 /* opt['model']['DFNet']['beta']                                    */
+    int32_t in_dim;                /* opt['model']['DFNet']['in_dim'] (126 with encoder, 84 without)   */
+    int32_t num_hidden;            /* len(opt['model']['DFNet']['dims'])                               */
+    int32_t dims[PNDF_MAX_HIDDEN]; /* opt['model']['DFNet']['dims']                                    */
+    int32_t device;                /* CUDA ordinal (opt['train']['device'])                            */
+} pndf_config;
+
+typedef struct pndf_handle pndf_handle;
+
+/* PoseNDF.__init__  (model/posendf.py:32-55).  Fails (non-zero) for architectures the fused kernel does
+ * not implement -- there is no fallback path. */
+int pndf_create(const pndf_config* cfg, pndf_handle** out);
+int pndf_destroy(pndf_handle* h);
+
+/* Number of fp32 parameters for cfg (1 365 565 for configs/amass.yaml), i.e. the length of the flat
+ * vector pndf_set_weights expects. */
+int pndf_param_count(const pndf_config* cfg, size_t* n);
+
+/* load_state_dict (experiments/sample_poses.py:90-91, model/train_posendf.py:158-176).
+ * `flat` is a HOST pointer to the state_dict tensors concatenated in the reference's own order:
+ *   enc.net.{i}.net.0.weight, .0.bias, .2.weight, .2.bias  for i = 0..20   (only if use_enc)
+ *   dfnet.lin{l}.weight (out,in row-major), dfnet.lin{l}.bias              for l = 0..num_hidden
+ * The library repacks it into the slab stream the kernel consumes and uploads it (synchronous). */
+int pndf_set_weights(pndf_handle* h, const float* flat, size_t n);
+
+/* PoseNDF.forward(pose, train=False)['dist_pred']  (model/posendf.py:62-76,100-101).
+ * normalise != 0 applies F.normalize(pose, dim=1) (posendf.py:71); normalise == 0 is the manifold
+ * branch of the train path (posendf.py:80-83).  dist_dev: B floats. */
+int pndf_forward(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, float* dist_dev, void* stream);
+
+/* forward + gradient(pose, dist_pred)  (model/posendf.py:18-27 / experiments/sample_poses.py:25-34,73;
+ * with an upstream gradient it is the backward of experiments/motion_denoise.py:98 through the prior).
+ * g_up_dev: B floats or NULL (= ones).  grad_dev: B*84 floats = g_up[b] * d dist[b] / d pose[b]. */
+int pndf_forward_grad(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, const float* g_up_dev,
+                      float* dist_dev, float* grad_dev, void* stream);
+
+/* The projection loop body, `steps` times, in one launch (experiments/sample_poses.py:70-74):
+ *     pose <- pose - dist * d dist / d pose
+ * renorm != 0 re-normalises every quaternion after each step (north-star option; the reference does
+ * not).  pose_dev is updated in place; dist_dev (B floats, may be NULL) receives the
+ * distance evaluated at the start of the last step, as the reference's loop leaves it. */
+int pndf_project(pndf_handle* h, float* pose_dev, int64_t B, int steps, int renorm, float* dist_dev, void* stream);
+
+/* Same as pndf_project but with HOST buffers (what a non-CUDA caller of the reference's
+ * SamplePose.project would hold): pinned staging, chunked H2D / kernel / D2H overlap inside.
+ * pose_out_host may alias pose_in_host.  Synchronous. */
+int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out_host, float* dist_host,
+                      int64_t B, int steps, int renorm);
+
+/* Motion-denoise prior term (experiments/motion_denoise.py:81-83,97-98):
+ *   quat = axis_angle_to_quaternion(aa)   (pytorch3d 0.7.2 formula), dist = PoseNDF(quat),
+ *   grad_aa = g_up[b] * d dist[b] / d aa[b]   (g_up NULL = ones).
+ * aa_dev: B*63 floats (21 joints x 3).  dist_dev: B floats.  grad_aa_dev: B*63 floats. */
+int pndf_prior_grad(pndf_handle* h, const float* aa_dev, int64_t B, const float* g_up_dev, float* dist_dev,
+                    float* grad_aa_dev, void* stream);
+
+/* Debug / test hook: like pndf_forward_grad for the first 32 poses only, additionally dumping every
+ * intermediate activation / gradient tile (layout documented in DESIGN.md) to dump_dev (floats). */
+int pndf_debug_dump_floats(size_t* n);
+int pndf_forward_grad_debug(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, float* dist_dev,
+                            float* grad_dev, float* dump_dev, void* stream);
+
+/* Measurement helpers used by bench.py (not on the data path):
+ *   pndf_fp32_peak: in-process FFMA micro-benchmark, dense fp32 FMA TFLOP/s of this GPU right now.
+ *     variant 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2).
+ *   pndf_launch_count: number of kernel launches this handle has enqueued so far. */
+int pndf_fp32_peak(int device, int variant, double* tflops);
+int pndf_launch_count(pndf_handle* h, int64_t* n);
+int pndf_num_sms(pndf_handle* h, int* n);
+
+const char* pndf_last_error(void);
+const char* pndf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNDF_H_ */

@@ -1,0 +1,414 @@
+// pndf_capi.cu -- C ABI (include/pndf.h) over the fused sm_100a kernel: handle management, host-side
+// repacking of the reference state_dict into the kernel's slab stream, launches, host-buffer pipeline.
+#include "../../include/pndf.h"
+#include "pndf_kernel.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pndf;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const std::string& msg) {
+    g_err = msg;
+    return 1;
+}
+#define CUDA_OK(expr)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+const int kAmassDims[6] = {256, 512, 1024, 512, 256, 64};
+
+}  // namespace
+
+struct pndf_handle {
+    pndf_config cfg;
+    int num_sms = 0;
+    bool have_weights = false;
+    float* d_wstream = nullptr;   // slab stream
+    size_t wstream_floats = 0;
+    float* d_small = nullptr;     // biases (2625) + w6 (64) + encoder (3516), each 16B-aligned
+    size_t off_bias[7];
+    size_t off_w6 = 0, off_enc = 0;
+    float* d_scratch = nullptr;   // softplus derivative scratch, num_sms * kUnits * 32 floats
+    int f0_slabs = 0, z0_rows = 0;
+    int64_t launches = 0;
+    // host pipeline (pndf_project_host)
+    cudaStream_t hs[2] = {nullptr, nullptr};
+    float* d_chunk[2] = {nullptr, nullptr};
+    float* d_chunk_dist[2] = {nullptr, nullptr};
+    int64_t chunk_poses = 0;
+};
+
+namespace {
+
+int validate(const pndf_config* c) {
+    if (!c) return fail("null config");
+    if (c->num_hidden != 6) return fail("fused kernel implements DFNet dims [256,512,1024,512,256,64] (configs/amass.yaml) only");
+    for (int i = 0; i < 6; ++i)
+        if (c->dims[i] != kAmassDims[i]) return fail("fused kernel implements DFNet dims [256,512,1024,512,256,64] (configs/amass.yaml) only");
+    if (c->use_enc && c->in_dim != 126) return fail("with the structure encoder DFNet.in_dim must be 126");
+    if (!c->use_enc && c->in_dim != 84) return fail("without the structure encoder DFNet.in_dim must be 84");
+    for (int a : {c->enc_act, c->df_act})
+        if (a < 0 || a > 2) return fail("activation must be PNDF_ACT_RELU / LRELU / SOFTPLUS");
+    return 0;
+}
+
+size_t param_count(const pndf_config* c) {
+    size_t n = c->use_enc ? (size_t)kEncFloats : 0;
+    int prev = c->in_dim;
+    for (int l = 0; l < 6; ++l) {
+        n += (size_t)prev * c->dims[l] + c->dims[l];
+        prev = c->dims[l];
+    }
+    n += prev + 1;
+    return n;
+}
+
+// Append one op's weights as slabs of KC rows x N floats.  get(k, n) returns w[k][n] (0 outside).
+template <class F>
+void pack_op(std::vector<float>& out, int K, int N, F get) {
+    const int KC = kSlabFloats / N;
+    for (int s = 0; s < K / KC; ++s)
+        for (int kk = 0; kk < KC; ++kk)
+            for (int n = 0; n < N; ++n) out.push_back(get(s * KC + kk, n));
+}
+
+int launch(pndf_handle* h, KParams& p, bool grad, cudaStream_t st) {
+    if (!h->have_weights) return fail("pndf_set_weights has not been called");
+    if (p.B <= 0) return 0;
+    p.wstream = h->d_wstream;
+    for (int l = 0; l < 7; ++l) p.bias[l] = h->d_small + h->off_bias[l];
+    p.w6 = h->d_small + h->off_w6;
+    p.encw = h->cfg.use_enc ? h->d_small + h->off_enc : nullptr;
+    p.dscratch = h->d_scratch;
+    p.ntiles = (int)((p.B + kTileM - 1) / kTileM);
+    p.use_enc = h->cfg.use_enc; p.enc_act = h->cfg.enc_act; p.df_act = h->cfg.df_act;
+    p.enc_beta = h->cfg.enc_beta; p.df_beta = h->cfg.df_beta;
+    p.f0_slabs = h->f0_slabs; p.z0_rows = h->z0_rows; p.in_dim = h->cfg.in_dim;
+    const int grid = std::min(p.ntiles, h->num_sms);
+    if (grad)
+        pndf_fused_kernel<true><<<grid, kThreads, kSmTotal, st>>>(p);
+    else
+        pndf_fused_kernel<false><<<grid, kThreads, kSmTotal, st>>>(p);
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pndf_last_error(void) { return g_err.c_str(); }
+const char* pndf_version(void) { return "posendf_b200 0.1 (sm_100a fused FFMA kernel)"; }
+
+int pndf_param_count(const pndf_config* cfg, size_t* n) {
+    if (validate(cfg)) return 1;
+    *n = param_count(cfg);
+    return 0;
+}
+
+int pndf_create(const pndf_config* cfg, pndf_handle** out) {
+    if (!out) return fail("null out pointer");
+    if (validate(cfg)) return 1;
+    int ndev = 0;
+    CUDA_OK(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("no such CUDA device");
+    CUDA_OK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(std::string("libpndf is built for sm_100a (B200); device is ") + prop.name);
+    pndf_handle* h = new pndf_handle();
+    h->cfg = *cfg;
+    h->num_sms = prop.multiProcessorCount;
+    h->z0_rows = cfg->use_enc ? 128 : 96;
+    h->f0_slabs = h->z0_rows / 16;
+    CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
+    CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
+    if (cfg->df_act == PNDF_ACT_SOFTPLUS)
+        CUDA_OK(cudaMalloc(&h->d_scratch, (size_t)h->num_sms * kUnits * 32 * sizeof(float)));
+    *out = h;
+    return 0;
+}
+
+int pndf_destroy(pndf_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->d_wstream);
+    cudaFree(h->d_small);
+    cudaFree(h->d_scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+        cudaFree(h->d_chunk[i]);
+        cudaFree(h->d_chunk_dist[i]);
+    }
+    delete h;
+    return 0;
+}
+
+int pndf_set_weights(pndf_handle* h, const float* flat, size_t n) {
+    if (!h || !flat) return fail("null argument");
+    if (n != param_count(&h->cfg)) return fail("pndf_set_weights: wrong parameter count");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    const float* enc = nullptr;
+    const float* cur = flat;
+    if (h->cfg.use_enc) {
+        enc = cur;
+        cur += kEncFloats;
+    }
+    const int in0 = h->cfg.in_dim;
+    const int widths[8] = {in0, 256, 512, 1024, 512, 256, 64, 1};
+    const float* W[7];
+    const float* Bv[7];
+    for (int l = 0; l < 7; ++l) {
+        W[l] = cur; cur += (size_t)widths[l + 1] * widths[l];
+        Bv[l] = cur; cur += widths[l + 1];
+    }
+    // ---- slab stream, in consumption order (pndf_kernel.cuh)
+    std::vector<float> s;
+    s.reserve((size_t)700 * kSlabFloats);
+    auto fwd = [&](int l, int k_off, int n_off) {   // w(k,n) = W_l[n_off+n][k_off+k]
+        const float* w = W[l]; const int in = widths[l], out = widths[l + 1];
+        return [=](int k, int n) { return (k_off + k < in && n_off + n < out) ? w[(size_t)(n_off + n) * in + (k_off + k)] : 0.0f; };
+    };
+    auto bwd = [&](int l, int k_off, int n_off) {   // w(k,n) = W_l[k_off+k][n_off+n]
+        const float* w = W[l]; const int in = widths[l], out = widths[l + 1];
+        return [=](int k, int n) { return (k_off + k < out && n_off + n < in) ? w[(size_t)(k_off + k) * in + (n_off + n)] : 0.0f; };
+    };
+    pack_op(s, h->z0_rows, 256, fwd(0, 0, 0));       // F0
+    pack_op(s, 256, 512, fwd(1, 0, 0));              // F1
+    pack_op(s, 512, 512, fwd(2, 0, 0));              // F2a : out features [0,512)
+    pack_op(s, 512, 512, fwd(3, 0, 0));              // F3a : in  features [0,512)
+    pack_op(s, 512, 512, fwd(2, 0, 512));            // F2b : out features [512,1024)
+    pack_op(s, 512, 512, fwd(3, 512, 0));            // F3b : in  features [512,1024)
+    pack_op(s, 512, 256, fwd(4, 0, 0));              // F4
+    pack_op(s, 256, 64, fwd(5, 0, 0));               // F5
+    pack_op(s, 64, 256, bwd(5, 0, 0));               // B5
+    pack_op(s, 256, 512, bwd(4, 0, 0));              // B4
+    pack_op(s, 512, 512, bwd(3, 0, 0));              // B3a : in  features [0,512) of layer 3
+    pack_op(s, 512, 512, bwd(2, 0, 0));              // B2a : out features [0,512) of layer 2
+    pack_op(s, 512, 512, bwd(3, 0, 512));            // B3b
+    pack_op(s, 512, 512, bwd(2, 512, 0));            // B2b
+    pack_op(s, 512, 256, bwd(1, 0, 0));              // B1
+    pack_op(s, 256, 128, bwd(0, 0, 0));              // B0 (in_dim padded to 128)
+    const size_t expect = (size_t)(h->f0_slabs + 32 + 256 + 32 + 4 + 4 + 32 + 256 + 32 + 8) * kSlabFloats;
+    if (s.size() != expect) return fail("internal: slab stream size mismatch");
+    // ---- small parameters
+    std::vector<float> sm;
+    auto align4 = [&]() { while (sm.size() % 4) sm.push_back(0.0f); };
+    for (int l = 0; l < 7; ++l) {
+        align4();
+        h->off_bias[l] = sm.size();
+        sm.insert(sm.end(), Bv[l], Bv[l] + widths[l + 1]);
+    }
+    align4(); h->off_w6 = sm.size(); sm.insert(sm.end(), W[6], W[6] + 64);
+    align4(); h->off_enc = sm.size();
+    if (enc) sm.insert(sm.end(), enc, enc + kEncFloats);
+    align4();
+    if (!h->d_wstream) CUDA_OK(cudaMalloc(&h->d_wstream, s.size() * sizeof(float)));
+    if (!h->d_small) CUDA_OK(cudaMalloc(&h->d_small, sm.size() * sizeof(float)));
+    h->wstream_floats = s.size();
+    CUDA_OK(cudaMemcpy(h->d_wstream, s.data(), s.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->d_small, sm.data(), sm.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->have_weights = true;
+    return 0;
+}
+
+int pndf_forward(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, float* dist_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (B == 0) return 0;
+    if (B < 0 || !pose_dev || !dist_dev) return fail("null argument");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    KParams p{};
+    p.pose_in = pose_dev; p.dist = dist_dev; p.B = B; p.steps = 1; p.normalise = normalise; p.input_kind = IN_QUAT;
+    return launch(h, p, false, (cudaStream_t)stream);
+}
+
+int pndf_forward_grad(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, const float* g_up_dev,
+                      float* dist_dev, float* grad_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (B == 0) return 0;
+    if (B < 0 || !pose_dev || !grad_dev) return fail("null argument");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    KParams p{};
+    p.pose_in = pose_dev; p.dist = dist_dev; p.grad = grad_dev; p.g_up = g_up_dev; p.B = B; p.steps = 1;
+    p.normalise = normalise; p.input_kind = IN_QUAT;
+    return launch(h, p, true, (cudaStream_t)stream);
+}
+
+int pndf_project(pndf_handle* h, float* pose_dev, int64_t B, int steps, int renorm, float* dist_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (steps < 1) return fail("steps must be >= 1");
+    if (B == 0) return 0;
+    if (B < 0 || !pose_dev) return fail("null argument");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    KParams p{};
+    p.pose_in = pose_dev; p.pose_out = pose_dev; p.dist = dist_dev; p.B = B; p.steps = steps; p.do_step = 1;
+    p.renorm = renorm; p.normalise = 1; p.input_kind = IN_QUAT;
+    return launch(h, p, true, (cudaStream_t)stream);
+}
+
+int pndf_prior_grad(pndf_handle* h, const float* aa_dev, int64_t B, const float* g_up_dev, float* dist_dev,
+                    float* grad_aa_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (B == 0) return 0;
+    if (B < 0 || !aa_dev || !grad_aa_dev) return fail("null argument");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    KParams p{};
+    p.pose_in = aa_dev; p.dist = dist_dev; p.grad = grad_aa_dev; p.g_up = g_up_dev; p.B = B; p.steps = 1;
+    p.normalise = 1; p.input_kind = IN_AXIS_ANGLE;
+    return launch(h, p, true, (cudaStream_t)stream);
+}
+
+int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out_host, float* dist_host, int64_t B,
+                      int steps, int renorm) {
+    if (!h) return fail("null handle");
+    if (steps < 1) return fail("steps must be >= 1");
+    if (B == 0) return 0;
+    if (B < 0 || !pose_in_host || !pose_out_host) return fail("null argument");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    const int64_t chunk = (int64_t)h->num_sms * 4 * kTileM;
+    if (!h->hs[0]) {
+        for (int i = 0; i < 2; ++i) {
+            CUDA_OK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
+            CUDA_OK(cudaMalloc(&h->d_chunk[i], chunk * 84 * sizeof(float)));
+            CUDA_OK(cudaMalloc(&h->d_chunk_dist[i], chunk * sizeof(float)));
+        }
+        h->chunk_poses = chunk;
+    }
+    int which = 0;
+    for (int64_t off = 0; off < B; off += chunk, which ^= 1) {
+        const int64_t nb = std::min(chunk, B - off);
+        cudaStream_t st = h->hs[which];
+        CUDA_OK(cudaMemcpyAsync(h->d_chunk[which], pose_in_host + off * 84, nb * 84 * sizeof(float), cudaMemcpyHostToDevice, st));
+        KParams p{};
+        p.pose_in = h->d_chunk[which]; p.pose_out = h->d_chunk[which]; p.dist = h->d_chunk_dist[which]; p.B = nb;
+        p.steps = steps; p.do_step = 1; p.renorm = renorm; p.normalise = 1; p.input_kind = IN_QUAT;
+        if (launch(h, p, true, st)) return 1;
+        CUDA_OK(cudaMemcpyAsync(pose_out_host + off * 84, h->d_chunk[which], nb * 84 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (dist_host) CUDA_OK(cudaMemcpyAsync(dist_host + off, h->d_chunk_dist[which], nb * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_OK(cudaStreamSynchronize(h->hs[0]));
+    CUDA_OK(cudaStreamSynchronize(h->hs[1]));
+    return 0;
+}
+
+int pndf_debug_dump_floats(size_t* n) {
+    *n = (size_t)kDumpRows * 32;
+    return 0;
+}
+
+int pndf_forward_grad_debug(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, float* dist_dev,
+                            float* grad_dev, float* dump_dev, void* stream) {
+    if (!h || !pose_dev || !grad_dev || !dump_dev) return fail("null argument");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    KParams p{};
+    p.pose_in = pose_dev; p.dist = dist_dev; p.grad = grad_dev; p.B = std::min<int64_t>(B, 32); p.steps = 1;
+    p.normalise = normalise; p.input_kind = IN_QUAT; p.dbg = dump_dev;
+    return launch(h, p, true, (cudaStream_t)stream);
+}
+
+int pndf_launch_count(pndf_handle* h, int64_t* n) {
+    if (!h || !n) return fail("null argument");
+    *n = h->launches;
+    return 0;
+}
+int pndf_num_sms(pndf_handle* h, int* n) {
+    if (!h || !n) return fail("null argument");
+    *n = h->num_sms;
+    return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// fp32 FMA peak micro-benchmark (roofline denominator for an FFMA-bound kernel; measured, not nominal)
+namespace {
+
+template <int VARIANT>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float seed) {
+    // 8x8 register tile like the GEMM inner loop: 64 independent accumulators, operands in registers
+    float a[8], b[8], acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = seed + 0.001f * (threadIdx.x + i);
+        b[i] = seed - 0.002f * (threadIdx.x + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int rep = 0; rep < 4; ++rep) {
+        if (VARIANT == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                unsigned long long aa;
+                asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a[i]));
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    unsigned long long bb, cc;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b[j]), "f"(b[j + 1]));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(acc[i][j]), "f"(acc[i][j + 1]));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cc) : "l"(aa), "l"(bb));
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][j]), "=f"(acc[i][j + 1]) : "l"(cc));
+                }
+            }
+        }
+      }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace
+
+extern "C" int pndf_fp32_peak(int device, int variant, double* tflops) {
+    if (!tflops) return fail("null argument");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 2048;
+    float* out = nullptr;
+    CUDA_OK(cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_OK(cudaEventRecord(e0));
+        if (variant == 0)
+            fp32_peak_kernel<0><<<blocks, threads>>>(out, iters, 0.5f);
+        else
+            fp32_peak_kernel<1><<<blocks, threads>>>(out, iters, 0.5f);
+        CUDA_OK(cudaEventRecord(e1));
+        CUDA_OK(cudaEventSynchronize(e1));
+        CUDA_OK(cudaGetLastError());
+        float ms = 0.0f;
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * 4.0 * iters * (double)blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return 0;
+}

@@ -1,0 +1,867 @@
+// pndf_kernel.cuh -- the fused PoseNDF kernel for sm_100a (B200).
+//
+// One persistent CTA per SM.  A CTA owns a tile of 32 poses and walks the WHOLE network for it without
+// touching HBM in between:
+//
+//   load 32 poses -> column-normalise (model/posendf.py:71) -> structure encoder along the kinematic tree
+//   (model/network/net_modules.py:140-170) -> DFNet 126->256->512->1024->512->256->64->1
+//   (net_modules.py:46-72) -> analytic reverse pass (replaces torch.autograd.grad, model/posendf.py:18-27)
+//   -> normalise Jacobian -> x <- x - d * dd/dx (experiments/sample_poses.py:74), optionally K times.
+//
+// The DFNet layers (99.8 % of the flops) run as register-tiled fp32 FFMA GEMMs: 256 compute threads, each
+// owning an 8-pose x TN-feature micro-tile; activations live in shared memory as [feature][pose] with a
+// 16-byte XOR swizzle; weights are streamed from L2 through a 3-stage ring of 16 KB slabs filled by a
+// rotating elected lane with cp.async.bulk (TMA 1-D bulk copies) + mbarriers.  The host pre-packs all
+// weights into ONE linear "slab stream" in exactly the order the tile consumes them (forward layout
+// W^T[k][n] for the forward ops, native W[out][in] for the reverse ops), so the producer just walks
+// memory.  The 1024-wide layer never exists in full: L2's output is produced in two 512-feature chunks
+// that are consumed immediately as K-chunks of L3 (accumulators stay in registers); the reverse pass
+// mirrors this.  Activation derivatives are 1 bit per unit in shared memory for relu / lrelu and fp32
+// in an L2-resident per-CTA scratch for softplus.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pndf {
+
+constexpr int kTileM = 32;            // poses per CTA tile
+constexpr int kGemmThreads = 256;     // 8 compute warps; the weight-slab producer role rotates among them
+constexpr int kThreads = 256;         // (256 threads -> 255 registers/thread for the 2x64 fused accumulators)
+constexpr int kSlabFloats = 4096;     // 16 KB weight slab = KC x N floats, KC*N == 4096
+constexpr int kSlabBytes = kSlabFloats * 4;
+constexpr int kStages = 3;
+constexpr int kXS = 85;               // padded row stride of the pose tile
+constexpr int kMaskStride = 2656;     // bytes per pose-group plane of the derivative bit masks
+constexpr int kUnits = 2624;          // hidden units of the DFNet (256+512+1024+512+256+64)
+constexpr int kEncFloats = 3516;
+
+// unit offsets (mask / scratch index) of each hidden layer output z1..z6
+constexpr int kU1 = 0, kU2 = 256, kU3 = 768, kU4 = 1792, kU5 = 2304, kU6 = 2560;
+
+// shared memory carve-up (bytes)
+constexpr int kSmX = 0;
+constexpr int kSmY = kSmX + 512 * 32 * 4;
+constexpr int kSmRing = kSmY + 512 * 32 * 4;
+constexpr int kSmMask = kSmRing + kStages * kSlabBytes;
+constexpr int kSmEncW = kSmMask + 4 * kMaskStride;
+constexpr int kSmXs = kSmEncW + 3520 * 4;
+constexpr int kSmNrm = kSmXs + kTileM * kXS * 4;
+constexpr int kSmDv = kSmNrm + 4 * 32 * 4;
+constexpr int kSmBar = kSmDv + 2 * 32 * 4;
+constexpr int kSmTotal = kSmBar + 2 * kStages * 8 + 16;
+
+// debug dump row offsets ([row][32 poses] floats)
+constexpr int kDumpRows = 5504;
+
+enum { ACT_RELU = 0, ACT_LRELU = 1, ACT_SOFTPLUS = 2 };
+enum { IN_QUAT = 0, IN_AXIS_ANGLE = 1 };
+
+struct KParams {
+    const float* wstream;     // slab stream (forward ops then reverse ops)
+    const float* bias[7];     // dfnet.lin{l}.bias
+    const float* w6;          // dfnet.lin6.weight (64)
+    const float* encw;        // encoder params, reference order (3516 floats) or nullptr
+    const float* pose_in;     // B x 84 (or B x 63 axis-angle in prior mode)
+    float* pose_out;          // B x 84 or nullptr
+    float* dist;              // B or nullptr
+    float* grad;              // B x 84 (or B x 63 in prior mode) or nullptr
+    const float* g_up;        // B or nullptr
+    float* dscratch;          // per-CTA fp32 derivative scratch (softplus) or nullptr
+    float* dbg;               // debug dump or nullptr
+    long long B;
+    int ntiles;
+    int steps;                // projection steps fused in this launch (>=1)
+    int do_step;              // apply x <- x - d*g
+    int renorm;               // per-quaternion renormalise after the step
+    int normalise;            // F.normalize(dim=1) on input
+    int input_kind;           // IN_QUAT / IN_AXIS_ANGLE
+    int use_enc, enc_act, df_act;
+    float enc_beta, df_beta;
+    int f0_slabs;             // slabs of the first forward op (z0 rows / 16)
+    int z0_rows;              // 128 (encoder) or 96 (raw 84 + pad)
+    int in_dim;               // 126 or 84
+};
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded spin: a mismatch between the producer's and the consumers' slab counts must end in a trap
+// (launch error), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void gemm_bar() { __syncthreads(); }
+
+// ------------------------------------------------------------------------------------------------ helpers
+// activations are stored [row = feature][32 poses]; the 16-byte chunk (4 poses) index is XOR-ed with
+// (row>>2)&7 so that the 8 lanes of a warp that own different feature groups hit different banks.
+__device__ __forceinline__ int swz(int row, int m) { return row * 32 + (((((m >> 2) ^ (row >> 2)) & 7) << 2) | (m & 3)); }
+
+__device__ __forceinline__ float act_eval(float v, int kind, float beta, float& deriv) {
+    if (kind == ACT_SOFTPLUS) {
+        float bx = v * beta;
+        if (bx > 20.0f) {
+            deriv = 1.0f;
+            return v;
+        }
+        float e = expf(bx);
+        deriv = e / (e + 1.0f);
+        return log1pf(e) / beta;
+    }
+    float slope = (kind == ACT_RELU) ? 0.0f : 0.01f;
+    bool pos = v > 0.0f;
+    deriv = pos ? 1.0f : slope;
+    return pos ? v : v * slope;
+}
+
+// Consumer position in the slab ring plus the bookkeeping every thread carries (identically) so that
+// whichever warp is elected for slab g can issue the prefetch of slab g + kStages - 1.
+struct Pipe {
+    uint32_t stage;       // ring slot of the slab being consumed
+    uint32_t phase;       // its mbarrier phase parity
+    uint32_t g;           // slabs consumed so far by this CTA
+    uint32_t pf_left;     // slabs not yet issued
+    uint32_t pf_pos;      // position (in slabs) of the next slab to issue inside the per-step stream
+    uint32_t step_slabs;  // slabs per network pass
+    const char* wsrc;     // slab stream base
+    __device__ __forceinline__ void advance() {
+        ++g;
+        if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+        }
+    }
+};
+
+struct Ctx {
+    float* X;
+    float* Y;
+    const float* ring;
+    uint8_t* mask;
+    uint64_t* full;
+    uint64_t* empty;
+    float* dscr;   // this CTA's derivative scratch (softplus) or nullptr
+    int tid, lane, mg, ng;
+    int df_act;
+    float df_beta;
+};
+
+template <int TN>
+__device__ __forceinline__ int feat_of(int ng, int j) {
+    if (TN == 8) return (j < 4) ? (ng * 4 + j) : (256 + ng * 4 + (j - 4));
+    if (TN == 4) return ng * 4 + j;
+    if (TN == 2) return ng * 2 + j;
+    return ng;
+}
+
+template <int TN>
+__device__ __forceinline__ void acc_init_bias(float (&acc)[8][TN], const float* __restrict__ bias, int ng, int nreal) {
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        int f = feat_of<TN>(ng, j);
+        float b = (f < nreal) ? __ldg(bias + f) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][j] = b;
+    }
+}
+template <int TN>
+__device__ __forceinline__ void acc_zero(float (&acc)[8][TN]) {
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i][j] = 0.0f;
+}
+
+// acc[8 poses][TN feats] += in[k][pose] * w[k][feat] over nslabs weight slabs (KC = 4096/(64*TN) rows each)
+template <int TN>
+__device__ __forceinline__ void gemm_op(float (&acc)[8][TN], const float* __restrict__ in, int nslabs, Pipe& pipe,
+                                        const Ctx& c) {
+    constexpr int N = 64 * TN;
+    constexpr int KC = kSlabFloats / N;
+    const int mg2 = c.mg * 2;
+    for (int s = 0; s < nslabs; ++s) {
+        // producer duty (rotates over the warps): refill the slot freed by slab g-1 with slab g+kStages-1
+        if (pipe.pf_left != 0) {
+            if (c.lane == 0 && (pipe.g & 7u) == (uint32_t)(c.tid >> 5)) {
+                const uint32_t slot = (pipe.stage == 0) ? (kStages - 1) : (pipe.stage - 1);
+                if (pipe.g != 0) mbar_wait(&c.empty[slot], (pipe.stage == 0) ? (pipe.phase ^ 1u) : pipe.phase);
+                mbar_arrive_expect_tx(&c.full[slot], kSlabBytes);
+                bulk_g2s(const_cast<float*>(c.ring) + slot * kSlabFloats, pipe.wsrc + (size_t)pipe.pf_pos * kSlabBytes, kSlabBytes,
+                         &c.full[slot]);
+            }
+            --pipe.pf_left;
+            if (++pipe.pf_pos == pipe.step_slabs) pipe.pf_pos = 0;
+        }
+        mbar_wait(&c.full[pipe.stage], pipe.phase);
+        const float* __restrict__ w = c.ring + pipe.stage * kSlabFloats;
+        const float* __restrict__ rowbase = in + (s * KC) * 32;
+        const int kb = ((s * KC) >> 2) & 7;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const int key = (kb + (kk >> 2)) & 7;
+            const float* row = rowbase + kk * 32;
+            const float4 a0 = *reinterpret_cast<const float4*>(row + (((mg2) ^ key) << 2));
+            const float4 a1 = *reinterpret_cast<const float4*>(row + (((mg2 + 1) ^ key) << 2));
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float b[TN];
+            if (TN == 8) {
+                const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + c.ng * 4);
+                const float4 b1 = *reinterpret_cast<const float4*>(w + kk * N + 256 + c.ng * 4);
+                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+                b[4 % TN] = b1.x; b[5 % TN] = b1.y; b[6 % TN] = b1.z; b[7 % TN] = b1.w;
+            } else if (TN == 4) {
+                const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + c.ng * 4);
+                b[0] = b0.x; b[1 % TN] = b0.y; b[2 % TN] = b0.z; b[3 % TN] = b0.w;
+            } else if (TN == 2) {
+                const float2 b0 = *reinterpret_cast<const float2*>(w + kk * N + c.ng * 2);
+                b[0] = b0.x; b[1 % TN] = b0.y;
+            } else {
+                b[0] = w[kk * N + c.ng];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncwarp();
+        if (c.lane == 0) mbar_arrive(&c.empty[pipe.stage]);
+        pipe.advance();
+    }
+}
+
+// write one feature row segment (8 poses of this thread) into a [feature][pose] buffer
+__device__ __forceinline__ void store_row8(float* buf, int f, int mg, const float (&v)[8]) {
+    const int key = (f >> 2) & 7;
+    float* row = buf + f * 32;
+    *reinterpret_cast<float4*>(row + (((mg * 2) ^ key) << 2)) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(row + (((mg * 2 + 1) ^ key) << 2)) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+template <int TN>
+__device__ __forceinline__ void mask_store(uint8_t* mask, int mg, int unit0, const uint32_t (&bits)[TN]) {
+    // units of one thread are consecutive in groups of min(TN,4)
+    uint8_t* base = mask + mg * kMaskStride;
+    if (TN >= 4) {
+#pragma unroll
+        for (int h = 0; h < TN / 4; ++h) {
+            uint32_t wv = bits[h * 4] | (bits[h * 4 + 1] << 8) | (bits[h * 4 + 2] << 16) | (bits[h * 4 + 3] << 24);
+            *reinterpret_cast<uint32_t*>(base + unit0 + h * 256) = wv;
+        }
+    } else if (TN == 2) {
+        *reinterpret_cast<uint16_t*>(base + unit0) = (uint16_t)(bits[0] | (bits[1 % TN] << 8));
+    } else {
+        base[unit0] = (uint8_t)bits[0];
+    }
+}
+template <int TN>
+__device__ __forceinline__ void mask_load(const uint8_t* mask, int mg, int unit0, uint32_t (&bits)[TN]) {
+    const uint8_t* base = mask + mg * kMaskStride;
+    if (TN >= 4) {
+#pragma unroll
+        for (int h = 0; h < TN / 4; ++h) {
+            uint32_t wv = *reinterpret_cast<const uint32_t*>(base + unit0 + h * 256);
+            bits[h * 4] = wv & 0xff; bits[h * 4 + 1] = (wv >> 8) & 0xff; bits[h * 4 + 2] = (wv >> 16) & 0xff; bits[h * 4 + 3] = wv >> 24;
+        }
+    } else if (TN == 2) {
+        uint32_t wv = *reinterpret_cast<const uint16_t*>(base + unit0);
+        bits[0] = wv & 0xff; bits[1 % TN] = wv >> 8;
+    } else {
+        bits[0] = base[unit0];
+    }
+}
+
+// forward epilogue: z = act(acc) (bias already in acc), remember the derivative, store z as next input.
+// unit_base: index of feature 0 of this op in the mask / scratch unit space.
+template <int TN>
+__device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* out, int unit_base, const Ctx& c, bool keep_deriv) {
+    const int unit0 = unit_base + feat_of<TN>(c.ng, 0);
+    if (c.df_act == ACT_SOFTPLUS) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int f = feat_of<TN>(c.ng, j);
+            float z[8], dv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[i] = act_eval(acc[i][j], ACT_SOFTPLUS, c.df_beta, dv[i]);
+            store_row8(out, f, c.mg, z);
+            if (keep_deriv) {
+                float* p = c.dscr + (size_t)(unit_base + f) * 32 + c.mg * 8;
+                *reinterpret_cast<float4*>(p) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+                *reinterpret_cast<float4*>(p + 4) = make_float4(dv[4], dv[5], dv[6], dv[7]);
+            }
+        }
+    } else {
+        const float slope = (c.df_act == ACT_RELU) ? 0.0f : 0.01f;
+        uint32_t bits[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int f = feat_of<TN>(c.ng, j);
+            float z[8];
+            uint32_t bm = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float v = acc[i][j];
+                const bool pos = v > 0.0f;
+                bm |= (pos ? 1u : 0u) << i;
+                z[i] = pos ? v : v * slope;
+            }
+            bits[j] = bm;
+            store_row8(out, f, c.mg, z);
+        }
+        if (keep_deriv) mask_store<TN>(c.mask, c.mg, unit0, bits);
+    }
+}
+
+// reverse epilogue: g = acc * act'(pre) of the layer whose input-gradient this op produced; store as the
+// next reverse op's input.  unit_base < 0: no derivative (the encoder features, handled by the encoder).
+template <int TN>
+__device__ __forceinline__ void epilogue_bwd(const float (&acc)[8][TN], float* out, int unit_base, const Ctx& c) {
+    if (unit_base < 0) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = acc[i][j];
+            store_row8(out, feat_of<TN>(c.ng, j), c.mg, v);
+        }
+        return;
+    }
+    if (c.df_act == ACT_SOFTPLUS) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int f = feat_of<TN>(c.ng, j);
+            const float* p = c.dscr + (size_t)(unit_base + f) * 32 + c.mg * 8;
+            const float4 d0 = *reinterpret_cast<const float4*>(p);
+            const float4 d1 = *reinterpret_cast<const float4*>(p + 4);
+            const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = acc[i][j] * dv[i];
+            store_row8(out, f, c.mg, v);
+        }
+    } else {
+        const float slope = (c.df_act == ACT_RELU) ? 0.0f : 0.01f;
+        uint32_t bits[TN];
+        mask_load<TN>(c.mask, c.mg, unit_base + feat_of<TN>(c.ng, 0), bits);
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = ((bits[j] >> i) & 1u) ? acc[i][j] : acc[i][j] * slope;
+            store_row8(out, feat_of<TN>(c.ng, j), c.mg, v);
+        }
+    }
+}
+
+__device__ __forceinline__ void dump_rows(float* dbg, int row0, const float* buf, int rows, int tid) {
+    if (dbg == nullptr) return;
+    for (int idx = tid; idx < rows * 32; idx += kGemmThreads) {
+        const int r = idx >> 5, m = idx & 31;
+        dbg[(size_t)(row0 + r) * 32 + m] = buf[swz(r, m)];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ encoder
+__constant__ int c_parent[21] = {-1, -1, -1, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19};
+
+__device__ __forceinline__ int enc_off(int i) { return (i < 3) ? i * 116 : 348 + (i - 3) * 176; }
+
+// one bone MLP (net_modules.py:86-111) for pose `m`: u (4 or 10) -> h (10) -> f (6); optionally returns
+// the activation derivatives at both layers.
+template <bool kDeriv>
+__device__ __forceinline__ void bone_mlp(const float* __restrict__ w, bool root, const float (&u)[10], int act, float beta,
+                                         float (&h)[10], float (&f)[6], float (&d1)[10], float (&d2)[6]) {
+    const int fin = root ? 4 : 10;
+    const float* w1 = w;
+    const float* b1 = w + 10 * fin;
+    const float* w2 = b1 + 10;
+    const float* b2 = w2 + 60;
+#pragma unroll
+    for (int o = 0; o < 10; ++o) {
+        float s = b1[o];
+        if (root) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s = fmaf(w1[o * 4 + k], u[k], s);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) s = fmaf(w1[o * 10 + k], u[k], s);
+        }
+        float dv;
+        h[o] = act_eval(s, act, beta, dv);
+        if (kDeriv) d1[o] = dv;
+    }
+#pragma unroll
+    for (int o = 0; o < 6; ++o) {
+        float s = b2[o];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) s = fmaf(w2[o * 10 + k], h[k], s);
+        float dv;
+        f[o] = act_eval(s, act, beta, dv);
+        if (kDeriv) d2[o] = dv;
+    }
+}
+
+// q_i of pose m from the raw pose tile and the column norms
+__device__ __forceinline__ void load_q(const float* xs, const float* nrm, int m, int i, bool normalise, float (&u)[10]) {
+#pragma unroll
+    for (int cpt = 0; cpt < 4; ++cpt) {
+        float x = xs[m * kXS + i * 4 + cpt];
+        u[cpt] = normalise ? x / nrm[cpt * 32 + m] : x;
+    }
+}
+
+// forward encoder for pose `m` (one lane per pose); writes features as rows [i*6+o][m] of `feat`.
+__device__ __forceinline__ void encoder_forward(const float* encw, const float* xs, const float* nrm, float* feat, int m,
+                                                const KParams& p) {
+    for (int i = 0; i < 21; ++i) {
+        const int par = c_parent[i];
+        float u[10], h[10], f[6], d1[10], d2[6];
+        load_q(xs, nrm, m, i, p.normalise != 0, u);
+        if (par >= 0) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) u[4 + r] = feat[swz(par * 6 + r, m)];
+        }
+        bone_mlp<false>(encw + enc_off(i), par < 0, u, p.enc_act, p.enc_beta, h, f, d1, d2);
+#pragma unroll
+        for (int o = 0; o < 6; ++o) feat[swz(i * 6 + o, m)] = f[o];
+    }
+}
+
+// reverse encoder for pose `m`: features in `feat` (recomputed), feature gradients in rows [0,126) of
+// `gbuf` (accumulated in place), quaternion gradients written to rows [128+e] of `gbuf`.
+__device__ __forceinline__ void encoder_backward(const float* encw, const float* xs, const float* nrm, const float* feat,
+                                                 float* gbuf, int m, const KParams& p) {
+    for (int i = 20; i >= 0; --i) {
+        const int par = c_parent[i];
+        const bool root = par < 0;
+        float u[10], h[10], f[6], d1[10], d2[6];
+        load_q(xs, nrm, m, i, p.normalise != 0, u);
+        if (!root) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) u[4 + r] = feat[swz(par * 6 + r, m)];
+        }
+        const float* w = encw + enc_off(i);
+        bone_mlp<true>(w, root, u, p.enc_act, p.enc_beta, h, f, d1, d2);
+        const int fin = root ? 4 : 10;
+        const float* w1 = w;
+        const float* w2 = w + 10 * fin + 10;
+        float t[6];
+#pragma unroll
+        for (int o = 0; o < 6; ++o) t[o] = gbuf[swz(i * 6 + o, m)] * d2[o];
+        float s1[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            float s = 0.0f;
+#pragma unroll
+            for (int o = 0; o < 6; ++o) s = fmaf(t[o], w2[o * 10 + k], s);
+            s1[k] = s * d1[k];
+        }
+        if (root) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float s = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) s = fmaf(s1[k], w1[k * 4 + j], s);
+                gbuf[swz(128 + i * 4 + j, m)] = s;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                float s = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) s = fmaf(s1[k], w1[k * 10 + j], s);
+                if (j < 4)
+                    gbuf[swz(128 + i * 4 + j, m)] = s;
+                else
+                    gbuf[swz(par * 6 + (j - 4), m)] += s;
+            }
+        }
+    }
+}
+
+// pytorch3d 0.7.2 axis_angle_to_quaternion (formula restated; source not in the reference tree)
+__device__ __forceinline__ void aa_to_quat(const float (&a)[3], float (&q)[4]) {
+    const float ang = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    const float half = 0.5f * ang;
+    const float k = (fabsf(ang) < 1e-6f) ? (0.5f - ang * ang / 48.0f) : (sinf(half) / ang);
+    q[0] = cosf(half);
+    q[1] = a[0] * k; q[2] = a[1] * k; q[3] = a[2] * k;
+}
+__device__ __forceinline__ void aa_to_quat_vjp(const float (&a)[3], const float (&qb)[4], float (&ab)[3]) {
+    const float ang2 = a[0] * a[0] + a[1] * a[1] + a[2] * a[2];
+    const float ang = sqrtf(ang2);
+    const float half = 0.5f * ang;
+    const bool small = ang < 1e-6f;
+    const float sa = small ? 1.0f : ang;
+    const float s = sinf(half), co = cosf(half);
+    const float k = small ? (0.5f - ang2 / 48.0f) : (s / sa);
+    const float dk = small ? (-1.0f / 24.0f) : ((0.5f * co * sa - s) / (sa * sa * sa));
+    const float dot = qb[1] * a[0] + qb[2] * a[1] + qb[3] * a[2];
+    const float cw = qb[0] * (-0.5f * k) + dk * dot;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ab[j] = cw * a[j] + k * qb[1 + j];
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <bool kGrad>
+__global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float* X = reinterpret_cast<float*>(smem + kSmX);
+    float* Y = reinterpret_cast<float*>(smem + kSmY);
+    float* ring = reinterpret_cast<float*>(smem + kSmRing);
+    uint8_t* mask = smem + kSmMask;
+    float* encw = reinterpret_cast<float*>(smem + kSmEncW);
+    float* xs = reinterpret_cast<float*>(smem + kSmXs);
+    float* nrm = reinterpret_cast<float*>(smem + kSmNrm);
+    float* dval = reinterpret_cast<float*>(smem + kSmDv);   // [32] distance, [32] upstream*out_act'
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmBar);
+    uint64_t* empty = full + kStages;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kGemmThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (p.use_enc) {
+        for (int i = tid; i < kEncFloats; i += kThreads) encw[i] = __ldg(p.encw + i);
+    }
+    __syncthreads();
+
+    // forward ops: F0(f0_slabs) F1(32) [F2a(64) F3a(64) F2b(64) F3b(64)] F4(32) F5(4)
+    // reverse ops: B5(4) B4(32) [B3a(64) B2a(64) B3b(64) B2b(64)] B1(32) B0(8)
+    const int fwd_slabs = p.f0_slabs + 32 + 256 + 32 + 4;
+    const int bwd_slabs = 4 + 32 + 256 + 32 + 8;
+    const int step_slabs = fwd_slabs + (kGrad ? bwd_slabs : 0);
+
+    // ------------------------------------------------------------------ compute warps
+    Ctx c;
+    c.X = X; c.Y = Y; c.ring = ring; c.mask = mask; c.full = full; c.empty = empty;
+    c.tid = tid; c.lane = lane; c.mg = lane >> 3; c.ng = warp * 8 + (lane & 7);
+    c.df_act = p.df_act; c.df_beta = p.df_beta;
+    c.dscr = p.dscratch ? p.dscratch + (size_t)blockIdx.x * kUnits * 32 : nullptr;
+    const bool keep = kGrad;
+    Pipe pipe;
+    pipe.stage = 0; pipe.phase = 0; pipe.g = 0;
+    pipe.step_slabs = (uint32_t)step_slabs;
+    pipe.wsrc = reinterpret_cast<const char*>(p.wstream);
+    {
+        const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const uint32_t total = (uint32_t)my_tiles * (uint32_t)p.steps * (uint32_t)step_slabs;
+        // prologue: the first kStages-1 slabs
+        const uint32_t pro = min(total, (uint32_t)(kStages - 1));
+        if (tid == 0) {
+            for (uint32_t s = 0; s < pro; ++s) {
+                mbar_arrive_expect_tx(&full[s], kSlabBytes);
+                bulk_g2s(ring + s * kSlabFloats, pipe.wsrc + (size_t)s * kSlabBytes, kSlabBytes, &full[s]);
+            }
+        }
+        pipe.pf_left = total - pro;
+        pipe.pf_pos = pro % (uint32_t)step_slabs;
+    }
+
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const long long pose0 = (long long)tile * kTileM;
+        const int nvalid = (int)min((long long)kTileM, p.B - pose0);
+        float* dbg = (tile == 0) ? p.dbg : nullptr;
+
+        // ---- load the pose tile (coalesced), zero-fill the tail
+        if (p.input_kind == IN_QUAT) {
+            const float* src = p.pose_in + pose0 * 84;
+            for (int idx = tid; idx < kTileM * 84; idx += kGemmThreads) {
+                const int m = idx / 84, e = idx - m * 84;
+                xs[m * kXS + e] = (m < nvalid) ? __ldg(src + idx) : 0.0f;
+            }
+        } else {
+            const float* src = p.pose_in + pose0 * 63;
+            for (int idx = tid; idx < kTileM * 21; idx += kGemmThreads) {
+                const int m = idx / 21, j = idx - m * 21;
+                float a[3] = {0.f, 0.f, 0.f}, q[4];
+                if (m < nvalid) {
+                    a[0] = __ldg(src + idx * 3); a[1] = __ldg(src + idx * 3 + 1); a[2] = __ldg(src + idx * 3 + 2);
+                }
+                aa_to_quat(a, q);
+#pragma unroll
+                for (int cpt = 0; cpt < 4; ++cpt) xs[m * kXS + j * 4 + cpt] = (m < nvalid) ? q[cpt] : 0.0f;
+            }
+        }
+        gemm_bar();
+
+        for (int st = 0; st < p.steps; ++st) {
+            float* dbg_s = (st == 0) ? dbg : nullptr;
+            // ---- column norms + encoder (one lane per pose)
+            if (warp == 0) {
+                const int m = lane;
+                if (p.normalise) {
+#pragma unroll
+                    for (int cpt = 0; cpt < 4; ++cpt) {
+                        float s = 0.0f;
+                        for (int j = 0; j < 21; ++j) {
+                            const float x = xs[m * kXS + j * 4 + cpt];
+                            s = fmaf(x, x, s);
+                        }
+                        nrm[cpt * 32 + m] = fmaxf(sqrtf(s), 1e-12f);
+                    }
+                }
+                if (p.use_enc) {
+                    encoder_forward(encw, xs, nrm, X, m, p);
+                    X[swz(126, m)] = 0.0f;
+                    X[swz(127, m)] = 0.0f;
+                } else {
+                    for (int e = 0; e < 96; ++e) {
+                        float v = 0.0f;
+                        if (e < 84) {
+                            const float x = xs[m * kXS + e];
+                            v = p.normalise ? x / nrm[(e & 3) * 32 + m] : x;
+                        }
+                        X[swz(e, m)] = v;
+                    }
+                }
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 0, X, p.z0_rows, tid);
+
+            // ================================================================= forward
+            {   // F0: z0 (X) -> z1 (Y), 256 wide
+                float acc[8][4];
+                acc_init_bias<4>(acc, p.bias[0], c.ng, 256);
+                gemm_op<4>(acc, X, p.f0_slabs, pipe, c);
+                epilogue_fwd<4>(acc, Y, kU1, c, keep);
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 128, Y, 256, tid);
+            {   // F1: z1 (Y) -> z2 (X), 512 wide
+                float acc[8][8];
+                acc_init_bias<8>(acc, p.bias[1], c.ng, 512);
+                gemm_op<8>(acc, Y, 32, pipe, c);
+                epilogue_fwd<8>(acc, X, kU2, c, keep);
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 384, X, 512, tid);
+            {   // F2/F3 fused: z3 chunk (Y) is consumed at once as a K-chunk of layer 3; z4 -> X
+                float acc3[8][8];
+                acc_init_bias<8>(acc3, p.bias[3], c.ng, 512);
+                for (int ch = 0; ch < 2; ++ch) {
+                    float acc2[8][8];
+                    acc_init_bias<8>(acc2, p.bias[2] + ch * 512, c.ng, 512);
+                    gemm_op<8>(acc2, X, 64, pipe, c);
+                    epilogue_fwd<8>(acc2, Y, kU3 + ch * 512, c, keep);
+                    gemm_bar();
+                    dump_rows(dbg_s, 896 + ch * 512, Y, 512, tid);
+                    gemm_op<8>(acc3, Y, 64, pipe, c);
+                    gemm_bar();
+                }
+                epilogue_fwd<8>(acc3, X, kU4, c, keep);
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 1920, X, 512, tid);
+            {   // F4: z4 (X) -> z5 (Y), 256 wide
+                float acc[8][4];
+                acc_init_bias<4>(acc, p.bias[4], c.ng, 256);
+                gemm_op<4>(acc, X, 32, pipe, c);
+                epilogue_fwd<4>(acc, Y, kU5, c, keep);
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 2432, Y, 256, tid);
+            {   // F5: z5 (Y) -> z6 (X), 64 wide
+                float acc[8][1];
+                acc_init_bias<1>(acc, p.bias[5], c.ng, 64);
+                gemm_op<1>(acc, Y, 4, pipe, c);
+                epilogue_fwd<1>(acc, X, kU6, c, keep);
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 2688, X, 64, tid);
+            // L6 (64 -> 1) + output activation: one lane per pose
+            if (warp == 0) {
+                const int m = lane;
+                float s = __ldg(p.bias[6]);
+                for (int k = 0; k < 64; ++k) s = fmaf(__ldg(p.w6 + k), X[swz(k, m)], s);
+                float dv;
+                const float d = act_eval(s, (p.df_act == ACT_SOFTPLUS) ? ACT_SOFTPLUS : ACT_RELU, p.df_beta, dv);
+                dval[m] = d;
+                float gu = 1.0f;
+                if (p.g_up != nullptr && m < nvalid) gu = __ldg(p.g_up + pose0 + m);
+                dval[32 + m] = gu * dv;
+                if (p.dist != nullptr && m < nvalid && st == p.steps - 1) p.dist[pose0 + m] = d;
+            }
+            if (!kGrad) {
+                gemm_bar();
+                continue;
+            }
+            gemm_bar();
+
+            // ================================================================= reverse
+            // g6 = gs * W6 * act'(pre5)  -> Y rows [0,64)
+            for (int idx = tid; idx < 64 * 32; idx += kGemmThreads) {
+                const int k = idx >> 5, m = idx & 31;
+                float dv;
+                if (p.df_act == ACT_SOFTPLUS) {
+                    dv = c.dscr[(size_t)(kU6 + k) * 32 + m];
+                } else {
+                    const uint32_t b = mask[(m >> 3) * kMaskStride + kU6 + k];
+                    dv = ((b >> (m & 7)) & 1u) ? 1.0f : ((p.df_act == ACT_RELU) ? 0.0f : 0.01f);
+                }
+                Y[swz(k, m)] = dval[32 + m] * __ldg(p.w6 + k) * dv;
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 2752, Y, 64, tid);
+            {   // B5: g6 (Y,64) -> g5 (X,256)
+                float acc[8][4];
+                acc_zero<4>(acc);
+                gemm_op<4>(acc, Y, 4, pipe, c);
+                epilogue_bwd<4>(acc, X, kU5, c);
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 2816, X, 256, tid);
+            {   // B4: g5 (X,256) -> g4 (Y,512)
+                float acc[8][8];
+                acc_zero<8>(acc);
+                gemm_op<8>(acc, X, 32, pipe, c);
+                epilogue_bwd<8>(acc, Y, kU4, c);
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 3072, Y, 512, tid);
+            {   // B3/B2 fused: g3 chunk (X) is consumed at once as a K-chunk of B2; g2 -> Y
+                float accb2[8][8];
+                acc_zero<8>(accb2);
+                for (int ch = 0; ch < 2; ++ch) {
+                    float accb3[8][8];
+                    acc_zero<8>(accb3);
+                    gemm_op<8>(accb3, Y, 64, pipe, c);
+                    epilogue_bwd<8>(accb3, X, kU3 + ch * 512, c);
+                    gemm_bar();
+                    dump_rows(dbg_s, 3584 + ch * 512, X, 512, tid);
+                    gemm_op<8>(accb2, X, 64, pipe, c);
+                    gemm_bar();
+                }
+                epilogue_bwd<8>(accb2, Y, kU2, c);
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 4608, Y, 512, tid);
+            {   // B1: g2 (Y,512) -> g1 (X,256)
+                float acc[8][4];
+                acc_zero<4>(acc);
+                gemm_op<4>(acc, Y, 32, pipe, c);
+                epilogue_bwd<4>(acc, X, kU1, c);
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 5120, X, 256, tid);
+            {   // B0: g1 (X,256) -> g0 (Y,128)
+                float acc[8][2];
+                acc_zero<2>(acc);
+                gemm_op<2>(acc, X, 8, pipe, c);
+                epilogue_bwd<2>(acc, Y, -1, c);
+            }
+            gemm_bar();
+            dump_rows(dbg_s, 5376, Y, 128, tid);
+
+            // ---- encoder reverse + normalise Jacobian + step (one lane per pose)
+            if (warp == 0) {
+                const int m = lane;
+                if (p.use_enc) {
+                    encoder_forward(encw, xs, nrm, X, m, p);          // recompute features (X is free)
+                    encoder_backward(encw, xs, nrm, X, Y, m, p);      // qbar -> Y rows [128, 212)
+                } else {
+                    for (int e = 0; e < 84; ++e) Y[swz(128 + e, m)] = Y[swz(e, m)];
+                }
+                const float d = dval[m];
+                // xbar = (qbar - q <q,qbar>) / n   per component column  (Jacobian of F.normalize(dim=1))
+#pragma unroll
+                for (int cpt = 0; cpt < 4; ++cpt) {
+                    float n = 1.0f, dot = 0.0f;
+                    if (p.normalise) {
+                        n = nrm[cpt * 32 + m];
+                        for (int j = 0; j < 21; ++j) dot = fmaf(xs[m * kXS + j * 4 + cpt] / n, Y[swz(128 + j * 4 + cpt, m)], dot);
+                        if (n <= 1e-12f) dot = 0.0f;   // clamp active: map is x/eps, Jacobian is I/eps
+                    }
+                    for (int j = 0; j < 21; ++j) {
+                        const int e = j * 4 + cpt;
+                        const float x = xs[m * kXS + e];
+                        float g = Y[swz(128 + e, m)];
+                        if (p.normalise) g = (g - (x / n) * dot) / n;
+                        Y[swz(128 + e, m)] = g;
+                        if (p.do_step) xs[m * kXS + e] = __fsub_rn(x, __fmul_rn(d, g));   // two roundings, as torch's x - d*g
+                    }
+                }
+                if (p.do_step && p.renorm) {
+                    for (int j = 0; j < 21; ++j) {
+                        float s = 0.0f;
+#pragma unroll
+                        for (int cpt = 0; cpt < 4; ++cpt) s = fmaf(xs[m * kXS + j * 4 + cpt], xs[m * kXS + j * 4 + cpt], s);
+                        const float inv = 1.0f / sqrtf(s);
+#pragma unroll
+                        for (int cpt = 0; cpt < 4; ++cpt) xs[m * kXS + j * 4 + cpt] *= inv;
+                    }
+                }
+            }
+            gemm_bar();
+        }  // steps
+
+        // ---- write back (coalesced)
+        if (kGrad) {
+            if (p.grad != nullptr) {
+                if (p.input_kind == IN_QUAT) {
+                    float* dst = p.grad + pose0 * 84;
+                    for (int idx = tid; idx < nvalid * 84; idx += kGemmThreads) {
+                        const int m = idx / 84, e = idx - m * 84;
+                        dst[idx] = Y[swz(128 + e, m)];
+                    }
+                } else {
+                    const float* src = p.pose_in + pose0 * 63;
+                    float* dst = p.grad + pose0 * 63;
+                    for (int idx = tid; idx < nvalid * 21; idx += kGemmThreads) {
+                        const int m = idx / 21, j = idx - m * 21;
+                        const float a[3] = {__ldg(src + idx * 3), __ldg(src + idx * 3 + 1), __ldg(src + idx * 3 + 2)};
+                        const float qb[4] = {Y[swz(128 + j * 4, m)], Y[swz(128 + j * 4 + 1, m)], Y[swz(128 + j * 4 + 2, m)],
+                                             Y[swz(128 + j * 4 + 3, m)]};
+                        float ab[3];
+                        aa_to_quat_vjp(a, qb, ab);
+                        dst[idx * 3] = ab[0]; dst[idx * 3 + 1] = ab[1]; dst[idx * 3 + 2] = ab[2];
+                    }
+                }
+            }
+            if (p.pose_out != nullptr) {
+                float* dst = p.pose_out + pose0 * 84;
+                for (int idx = tid; idx < nvalid * 84; idx += kGemmThreads) {
+                    const int m = idx / 84, e = idx - m * 84;
+                    dst[idx] = xs[m * kXS + e];
+                }
+            }
+        }
+        gemm_bar();   // xs / Y are reused by the next tile
+    }
+}
+
+}  // namespace pndf

@@ -1,0 +1,136 @@
+"""Thin host-side wrapper of one libpndf handle working on torch CUDA tensors (device memory + streams are
+PyTorch's; all arithmetic is the library's fused sm_100a kernel)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Engine:
+    """One pndf_handle.  Inputs must be CUDA fp32 tensors on the handle's device (made contiguous here)."""
+
+    def __init__(self, device=0, **cfg_kw):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("posendf_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.cfg = _lib.make_config(device=self.device.index, **cfg_kw)
+        h = C.c_void_p()
+        _lib.check(self.lib.pndf_create(C.byref(self.cfg), C.byref(h)))
+        self._h = h
+        n = C.c_size_t()
+        _lib.check(self.lib.pndf_param_count(C.byref(self.cfg), C.byref(n)))
+        self.param_count = n.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.pndf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights
+    def set_weights_flat(self, flat):
+        flat = np.ascontiguousarray(np.asarray(flat, dtype=np.float32).reshape(-1))
+        _lib.check(self.lib.pndf_set_weights(self._h, flat.ctypes.data_as(C.c_void_p), flat.size))
+
+    # ---- helpers
+    def _prep(self, t, last):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == self.device):
+            raise RuntimeError(f"expected a CUDA tensor on {self.device}")
+        t = t.detach().to(torch.float32).reshape(-1, last).contiguous()
+        return t
+
+    def forward(self, pose, normalise=True):
+        x = self._prep(pose, 84)
+        B = x.shape[0]
+        dist = torch.empty(B, 1, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.pndf_forward(self._h, x.data_ptr(), B, int(normalise), dist.data_ptr(), _stream_ptr(self.device)))
+        return dist
+
+    def forward_grad(self, pose, g_up=None, normalise=True):
+        x = self._prep(pose, 84)
+        B = x.shape[0]
+        dist = torch.empty(B, 1, device=self.device, dtype=torch.float32)
+        grad = torch.empty(B, 21, 4, device=self.device, dtype=torch.float32)
+        gp = None
+        if g_up is not None:
+            g_up = self._prep(g_up, 1)
+            gp = g_up.data_ptr()
+        _lib.check(self.lib.pndf_forward_grad(self._h, x.data_ptr(), B, int(normalise), gp, dist.data_ptr(), grad.data_ptr(),
+                                              _stream_ptr(self.device)))
+        return dist, grad
+
+    def project_(self, pose, steps=1, renorm=False):
+        """in place on a contiguous fp32 CUDA tensor; returns the distance at the start of the last step."""
+        if not (pose.is_cuda and pose.dtype == torch.float32 and pose.is_contiguous() and pose.device == self.device):
+            raise RuntimeError("project_ needs a contiguous fp32 CUDA tensor on the engine's device")
+        B = pose.numel() // 84
+        dist = torch.empty(B, 1, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.pndf_project(self._h, pose.data_ptr(), B, int(steps), int(renorm), dist.data_ptr(),
+                                         _stream_ptr(self.device)))
+        return dist
+
+    def project_host(self, pose_host, steps=1, renorm=False, out=None, dist_out=None):
+        """HOST tensors in, HOST tensors out (pinned memory gives copy/compute overlap)."""
+        if pose_host.is_cuda or pose_host.dtype != torch.float32 or not pose_host.is_contiguous():
+            raise RuntimeError("project_host needs a contiguous fp32 CPU tensor")
+        B = pose_host.numel() // 84
+        out = out if out is not None else torch.empty_like(pose_host)
+        dist_out = dist_out if dist_out is not None else torch.empty(B, 1, dtype=torch.float32)
+        _lib.check(self.lib.pndf_project_host(self._h, pose_host.data_ptr(), out.data_ptr(), dist_out.data_ptr(), B, int(steps),
+                                              int(renorm)))
+        return out, dist_out
+
+    def prior_grad(self, aa, g_up=None):
+        a = self._prep(aa, 63)
+        B = a.shape[0]
+        dist = torch.empty(B, 1, device=self.device, dtype=torch.float32)
+        grad = torch.empty(B, 21, 3, device=self.device, dtype=torch.float32)
+        gp = None
+        if g_up is not None:
+            g_up = self._prep(g_up, 1)
+            gp = g_up.data_ptr()
+        _lib.check(self.lib.pndf_prior_grad(self._h, a.data_ptr(), B, gp, dist.data_ptr(), grad.data_ptr(), _stream_ptr(self.device)))
+        return dist, grad
+
+    def forward_grad_debug(self, pose, normalise=True):
+        x = self._prep(pose, 84)
+        B = min(x.shape[0], 32)
+        n = C.c_size_t()
+        _lib.check(self.lib.pndf_debug_dump_floats(C.byref(n)))
+        dump = torch.zeros(n.value // 32, 32, device=self.device, dtype=torch.float32)
+        dist = torch.empty(B, 1, device=self.device, dtype=torch.float32)
+        grad = torch.empty(B, 21, 4, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.pndf_forward_grad_debug(self._h, x.data_ptr(), B, int(normalise), dist.data_ptr(), grad.data_ptr(),
+                                                    dump.data_ptr(), _stream_ptr(self.device)))
+        return dist, grad, dump
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        _lib.check(self.lib.pndf_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def num_sms(self) -> int:
+        n = C.c_int()
+        _lib.check(self.lib.pndf_num_sms(self._h, C.byref(n)))
+        return n.value
+
+
+def fp32_peak_tflops(device=0, variant=0) -> float:
+    lib = _lib.load()
+    v = C.c_double()
+    _lib.check(lib.pndf_fp32_peak(int(device), int(variant), C.byref(v)))
+    return v.value

@@ -1,0 +1,218 @@
+"""GPU parity tests proper: the fused sm_100a kernel, called through the C ABI (libpndf.so), against the
+oracle on the same seeded inputs and against the committed golden vectors of the real reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import (assert_grad_parity, assert_pose_parity, case_cfg, case_inputs, golden_case_names, load_golden,
+                      per_pose_rel, rel_err)
+from oracle import posendf_numpy as onp
+from posendf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+CASES = golden_case_names()
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def make_engine(meta, params):
+    from posendf_b200.engine import Engine
+    cfg = case_cfg(meta)
+    eng = Engine(device=0, use_enc=cfg["use_enc"], enc_act=cfg["enc_act"], enc_beta=cfg["enc_beta"],
+                 df_act=cfg["df_act"], df_beta=cfg["df_beta"])
+    in_dim = 126 if cfg["use_enc"] else 84
+    eng.set_weights_flat(synth.flatten_params(params, in_dim=in_dim, use_enc=cfg["use_enc"]))
+    return eng
+
+
+def oracle_intermediates(params, poses, cfg):
+    """every tile the kernel's debug hook dumps, from the fp64 oracle: list of (name, row0, array[rows, B])"""
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    x = poses.astype(np.float64)
+    q, _ = onp.normalise_columns(x)
+    if cfg["use_enc"]:
+        z0, _ = onp.encoder_forward(p64, q, cfg)
+    else:
+        z0 = q.reshape(len(q), -1)
+    d, pres = onp.dfnet_forward(p64, z0, cfg)
+    zs = [onp.act(pr, cfg["df_act"], cfg["df_beta"]) for pr in pres[:-1]]
+    out = [("z0", 0, z0.T), ("z1", 128, zs[0].T), ("z2", 384, zs[1].T), ("z3a", 896, zs[2][:, :512].T),
+           ("z3b", 1408, zs[2][:, 512:].T), ("z4", 1920, zs[3].T), ("z5", 2432, zs[4].T), ("z6", 2688, zs[5].T)]
+    g = np.ones((len(x), 1)) * onp.dact(pres[-1], onp.out_act_kind(cfg["df_act"]), cfg["df_beta"])
+    g = g @ p64["dfnet.lin6.weight"]
+    gm = {}
+    for l in range(5, -1, -1):
+        gm[l + 1] = g * onp.dact(pres[l], cfg["df_act"], cfg["df_beta"])     # masked gradient wrt pre_l
+        g = gm[l + 1] @ p64[f"dfnet.lin{l}.weight"]
+    out += [("g6m", 2752, gm[6].T), ("g5m", 2816, gm[5].T), ("g4m", 3072, gm[4].T), ("g3a", 3584, gm[3][:, :512].T),
+            ("g3b", 4096, gm[3][:, 512:].T), ("g2m", 4608, gm[2].T), ("g1m", 5120, gm[1].T), ("g0", 5376, g.T)]
+    return out
+
+
+@pytest.mark.parametrize("name", ["lrelu_enc_s1", "softplus_enc_s3", "lrelu_noenc_s6"])
+def test_every_layer_tile_matches_oracle(name):
+    meta, z = load_golden(name)
+    cfg = case_cfg(meta)
+    params, poses = case_inputs(meta)
+    poses = poses[:32]
+    eng = make_engine(meta, params)
+    dist, grad, dump = eng.forward_grad_debug(torch.from_numpy(poses).cuda())
+    torch.cuda.synchronize()
+    dump = dump.cpu().numpy()
+    os.makedirs(OUT, exist_ok=True)
+    lines = []
+    worst = 0.0
+    for nm, row0, ref in oracle_intermediates(params, poses, cfg):
+        got = dump[row0:row0 + ref.shape[0]]
+        scale = np.abs(ref).max() + 1e-30
+        err = np.abs(got - ref).max() / scale
+        lines.append(f"{name:24s} {nm:5s} rows {ref.shape[0]:4d} max|ref| {scale:.3e} max err/scale {err:.3e}")
+        worst = max(worst, err)
+    with open(os.path.join(OUT, f"layers_{name}.txt"), "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print("\n".join(lines))
+    assert worst < 2e-5, "\n".join(lines)
+    assert np.max(rel_err(dist.cpu().numpy(), z["d64"][:32])) < 1e-5
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_distance_vs_reference_golden(name):
+    meta, z = load_golden(name)
+    params, poses = case_inputs(meta)
+    eng = make_engine(meta, params)
+    d = eng.forward(torch.from_numpy(poses).cuda()).cpu().numpy()
+    assert d.shape == (64, 1)
+    assert np.max(rel_err(d, z["d64"])) < 1e-5      # north-star bar: 1e-5 relative on the distance
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_grad_vs_reference_golden(name):
+    meta, z = load_golden(name)
+    params, poses = case_inputs(meta)
+    eng = make_engine(meta, params)
+    d, g = eng.forward_grad(torch.from_numpy(poses).cuda())
+    assert np.max(rel_err(d.cpu().numpy(), z["d64"])) < 1e-5
+    assert_grad_parity(g.cpu().numpy(), z["g64"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_projection_10_steps_vs_reference_golden(name):
+    """experiments/sample_poses.py:70-74, ten steps fused in ONE launch."""
+    meta, z = load_golden(name)
+    params, poses = case_inputs(meta)
+    eng = make_engine(meta, params)
+    x = torch.from_numpy(poses).cuda().contiguous()
+    dlast = eng.project_(x, steps=10)
+    assert_pose_parity(x.cpu().numpy(), z["proj64"])
+    assert np.max(rel_err(dlast.cpu().numpy(), z["proj_d64"][-1])) < 2e-5
+    # ten single-step launches == one ten-step launch, bit for bit
+    y = torch.from_numpy(poses).cuda().contiguous()
+    for _ in range(10):
+        eng.project_(y, steps=1)
+    assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("B", [1, 31, 32, 33, 1000, 4736 + 17])
+def test_ragged_batches_and_tile_independence(B):
+    """per-pose independence: any batch size, any position in the batch -> identical bits."""
+    meta, _ = load_golden("lrelu_enc_s1")
+    params, _ = case_inputs(meta)
+    eng = make_engine(meta, params)
+    poses = synth.make_poses(5, B)
+    x = torch.from_numpy(poses).cuda()
+    d, g = eng.forward_grad(x)
+    dref, gref = onp.forward_grad({k: v.astype(np.float64) for k, v in params.items()}, poses.astype(np.float64), case_cfg(meta))
+    assert np.max(rel_err(d.cpu().numpy(), dref)) < 1e-5
+    assert_grad_parity(g.cpu().numpy(), gref)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0)).cuda()
+    d2, g2 = eng.forward_grad(x[perm].contiguous())
+    assert torch.equal(d2, d[perm]) and torch.equal(g2, g[perm])
+    assert torch.equal(eng.forward(x), d)           # forward-only kernel == forward of the grad kernel
+
+
+def test_empty_batch():
+    meta, _ = load_golden("lrelu_enc_s1")
+    params, _ = case_inputs(meta)
+    eng = make_engine(meta, params)
+    d = eng.forward(torch.empty(0, 21, 4, device="cuda"))
+    assert d.shape == (0, 1)
+
+
+def test_upstream_gradient_vjp_and_no_normalise():
+    meta, _ = load_golden("relu_enc_s2")
+    cfg = case_cfg(meta)
+    params, _ = case_inputs(meta)
+    eng = make_engine(meta, params)
+    poses = synth.make_poses(21, 96, kind="noisy", sigma=0.25)
+    gup = (synth.normal(3, 96) * 3.0).astype(np.float32).reshape(96, 1)
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    d, g = eng.forward_grad(torch.from_numpy(poses).cuda(), g_up=torch.from_numpy(gup).cuda())
+    dref, gref = onp.forward_grad(p64, poses.astype(np.float64), cfg, g_up=gup.astype(np.float64))
+    assert np.max(rel_err(d.cpu().numpy(), dref)) < 1e-5
+    assert_grad_parity(g.cpu().numpy(), gref)
+    # manifold branch of the train path: no column normalisation (model/posendf.py:80-83)
+    d, g = eng.forward_grad(torch.from_numpy(poses).cuda(), normalise=False)
+    dref, gref = onp.forward_grad(p64, poses.astype(np.float64), cfg, normalise=False)
+    assert np.max(rel_err(d.cpu().numpy(), dref)) < 1e-5
+    assert_grad_parity(g.cpu().numpy(), gref)
+
+
+def test_renormalised_projection_option():
+    meta, _ = load_golden("lrelu_enc_s1")
+    cfg = case_cfg(meta)
+    params, poses = case_inputs(meta)
+    eng = make_engine(meta, params)
+    x = torch.from_numpy(poses).cuda().contiguous()
+    eng.project_(x, steps=5, renorm=True)
+    xref, _ = onp.project({k: v.astype(np.float64) for k, v in params.items()}, poses.astype(np.float64), cfg, steps=5, renorm=True)
+    assert_pose_parity(x.cpu().numpy(), xref)
+    assert np.allclose(np.linalg.norm(x.cpu().numpy(), axis=2), 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["lrelu_enc_s1", "softplus_enc_s3"])
+def test_prior_term_axis_angle(name):
+    """experiments/motion_denoise.py:81-83 + backward to the axis-angle pose."""
+    meta, _ = load_golden(name)
+    cfg = case_cfg(meta)
+    params, _ = case_inputs(meta)
+    eng = make_engine(meta, params)
+    aa = synth.make_axis_angle(4, 200)
+    aa[0, 0] = 0.0
+    gup = np.full((200, 1), 1e7 * 2 * 0.5 / 200, dtype=np.float32)
+    d, g = eng.prior_grad(torch.from_numpy(aa).cuda(), g_up=torch.from_numpy(gup).cuda())
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    a64 = aa.astype(np.float64)
+    quat = onp.axis_angle_to_quaternion(a64)
+    dref, qbar = onp.forward_grad(p64, quat, cfg, g_up=gup.astype(np.float64))
+    gref = onp.axis_angle_to_quaternion_vjp(a64, qbar)
+    assert np.max(rel_err(d.cpu().numpy(), dref)) < 1e-5
+    assert_grad_parity(g.cpu().numpy(), gref, tol=2e-5)
+
+
+def test_host_buffer_projection_matches_device_projection():
+    meta, _ = load_golden("lrelu_enc_s1")
+    params, _ = case_inputs(meta)
+    eng = make_engine(meta, params)
+    B = 148 * 4 * 32 + 1234
+    poses = torch.from_numpy(synth.make_poses(8, B)).pin_memory()
+    out, dist = eng.project_host(poses, steps=2)
+    x = poses.cuda().contiguous()
+    d = eng.project_(x, steps=2)
+    assert torch.equal(out, x.cpu()) and torch.equal(dist, d.cpu())
+
+
+def test_large_batch_properties():
+    """config-2 size (65 536 poses): d >= 0, finite, chunk results identical to the full-batch run."""
+    meta, _ = load_golden("lrelu_enc_s1")
+    params, _ = case_inputs(meta)
+    eng = make_engine(meta, params)
+    B = 65536
+    x = torch.from_numpy(synth.make_poses(123, B)).cuda()
+    d, g = eng.forward_grad(x)
+    assert torch.isfinite(d).all() and torch.isfinite(g).all() and (d >= 0).all()
+    d2, g2 = eng.forward_grad(x[20000:20000 + 777].contiguous())
+    assert torch.equal(d2, d[20000:20777]) and torch.equal(g2, g[20000:20777])
+    y = x.clone()
+    eng.project_(y, steps=1)
+    assert torch.equal(y, x - d.reshape(-1, 1, 1) * g)

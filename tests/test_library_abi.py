@@ -1,0 +1,52 @@
+"""CPU: libpndf.so loads and exports every symbol include/pndf.h declares (no compute without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    if not os.path.exists(os.path.join(ROOT, "posendf_b200", "libpndf.so")):
+        g.build()
+    from posendf_b200 import _lib
+    return _lib.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "pndf.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pndf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported(lib):
+    from posendf_b200 import _lib
+    names = header_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/pndf.h but not exported by libpndf.so"
+        assert n in _lib.SYMBOLS, f"{n} has no ctypes prototype in posendf_b200/_lib.py"
+
+
+def test_config_validation_and_param_count(lib):
+    from posendf_b200 import _lib
+    n = C.c_size_t()
+    assert lib.pndf_param_count(C.byref(_lib.make_config()), C.byref(n)) == 0 and n.value == 1365565
+    assert lib.pndf_param_count(C.byref(_lib.make_config(use_enc=False)), C.byref(n)) == 0
+    assert n.value == 1365565 - 3516 - 126 * 256 + 84 * 256
+    assert lib.pndf_param_count(C.byref(_lib.make_config(dims=(256, 256))), C.byref(n)) != 0
+    assert b"amass.yaml" in lib.pndf_last_error()
+    assert lib.pndf_param_count(C.byref(_lib.make_config(use_enc=True, in_dim=84)), C.byref(n)) != 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from posendf_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine(device=0)

@@ -1,0 +1,6 @@
+"""Print the in-process FFMA peak (scalar FFMA and packed FFMA2) -- roofline denominator probe."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from posendf_b200.engine import fp32_peak_tflops
+for v, n in ((0, "FFMA"), (1, "FFMA2")):
+    print(f"fp32 peak {n}: {fp32_peak_tflops(0, v):.2f} TFLOP/s", flush=True)
