@@ -247,10 +247,30 @@ __device__ __forceinline__ void gemm_op(float (&acc)[8][TN], const float* __rest
             } else {
                 b[0] = w[kk * N + c.ng];
             }
+            if (TN >= 2) {
+                // packed fp32x2 FMA (Blackwell FFMA2): the pose value is the scalar-broadcast operand, two adjacent
+                // features ride in one 64-bit register pair -> half the issue slots of scalar FFMA, same rounding.
+                unsigned long long bb[(TN + 1) / 2];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+                for (int j = 0; j < TN / 2; ++j) asm("mov.b64 %0, {%1, %2};" : "=l"(bb[j]) : "f"(b[2 * j]), "f"(b[(2 * j + 1) % TN]));
 #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int i = 0; i < 8; ++i) {
+                    unsigned long long aa;
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a[i]));
+#pragma unroll
+                    for (int j = 0; j < TN / 2; ++j) {
+                        unsigned long long cc;
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(acc[i][2 * j]), "f"(acc[i][(2 * j + 1) % TN]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cc) : "l"(aa), "l"(bb[j]));
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2 * j]), "=f"(acc[i][(2 * j + 1) % TN]) : "l"(cc));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            }
         }
         __syncwarp();
         if (c.lane == 0) mbar_arrive(&c.empty[pipe.stage]);
@@ -394,116 +414,123 @@ __constant__ int c_parent[21] = {-1, -1, -1, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12
 
 __device__ __forceinline__ int enc_off(int i) { return (i < 3) ? i * 116 : 348 + (i - 3) * 176; }
 
-// one bone MLP (net_modules.py:86-111) for pose `m`: u (4 or 10) -> h (10) -> f (6); optionally returns
-// the activation derivatives at both layers.
-template <bool kDeriv>
-__device__ __forceinline__ void bone_mlp(const float* __restrict__ w, bool root, const float (&u)[10], int act, float beta,
-                                         float (&h)[10], float (&f)[6], float (&d1)[10], float (&d2)[6]) {
+// The encoder runs with 8 lanes per pose (4 poses per warp, 32 poses per CTA over the 8 warps): lane l of a
+// pose owns hidden units {l, 8+l} of the bone MLP's first layer and output feature l of its second layer
+// (net_modules.py:86-111); vectors are exchanged with warp shuffles, features go through the [feature][pose]
+// shared-memory buffer so that children find their parent's feature (net_modules.py:162-168).
+struct EncLane {
+    int m;        // pose column in the tile
+    int l;        // lane within the 8-lane pose group
+    int base;     // first lane of the group inside the warp
+};
+
+__device__ __forceinline__ float grp_get(float v, int src_l, const EncLane& e) { return __shfl_sync(0xffffffffu, v, e.base + src_l); }
+
+// first part shared by forward and reverse: u, the two hidden units of this lane, all 10 hidden values, and this
+// lane's output feature (o = min(l,5)).  d1a/d1b/d2 = activation derivatives at this lane's units.
+__device__ __forceinline__ void bone_forward(const float* __restrict__ w, bool root, const float* xs, const float* nrm,
+                                             const float* feat, int i, int par, const EncLane& e, const KParams& p,
+                                             float (&u)[10], float (&h)[10], float& f, float& d1a, float& d1b, float& d2) {
     const int fin = root ? 4 : 10;
+#pragma unroll
+    for (int cpt = 0; cpt < 4; ++cpt) {
+        const float x = xs[e.m * kXS + i * 4 + cpt];
+        u[cpt] = p.normalise ? x / nrm[cpt * 32 + e.m] : x;
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) u[4 + r] = root ? 0.0f : feat[swz(par * 6 + r, e.m)];
+    const int oa = e.l, ob = min(8 + e.l, 9);
     const float* w1 = w;
     const float* b1 = w + 10 * fin;
     const float* w2 = b1 + 10;
     const float* b2 = w2 + 60;
+    float sa = b1[oa], sb = b1[ob];
+    if (root) {
 #pragma unroll
-    for (int o = 0; o < 10; ++o) {
-        float s = b1[o];
-        if (root) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) s = fmaf(w1[o * 4 + k], u[k], s);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 10; ++k) s = fmaf(w1[o * 10 + k], u[k], s);
+        for (int k = 0; k < 4; ++k) {
+            sa = fmaf(w1[oa * 4 + k], u[k], sa);
+            sb = fmaf(w1[ob * 4 + k], u[k], sb);
         }
-        float dv;
-        h[o] = act_eval(s, act, beta, dv);
-        if (kDeriv) d1[o] = dv;
-    }
+    } else {
 #pragma unroll
-    for (int o = 0; o < 6; ++o) {
-        float s = b2[o];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) s = fmaf(w2[o * 10 + k], h[k], s);
-        float dv;
-        f[o] = act_eval(s, act, beta, dv);
-        if (kDeriv) d2[o] = dv;
+        for (int k = 0; k < 10; ++k) {
+            sa = fmaf(w1[oa * 10 + k], u[k], sa);
+            sb = fmaf(w1[ob * 10 + k], u[k], sb);
+        }
     }
+    const float ha = act_eval(sa, p.enc_act, p.enc_beta, d1a);
+    const float hb = act_eval(sb, p.enc_act, p.enc_beta, d1b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[k] = grp_get(ha, k, e);
+    h[8] = grp_get(hb, 0, e);
+    h[9] = grp_get(hb, 1, e);
+    const int o = min(e.l, 5);
+    float s2 = b2[o];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) s2 = fmaf(w2[o * 10 + k], h[k], s2);
+    f = act_eval(s2, p.enc_act, p.enc_beta, d2);
 }
 
-// q_i of pose m from the raw pose tile and the column norms
-__device__ __forceinline__ void load_q(const float* xs, const float* nrm, int m, int i, bool normalise, float (&u)[10]) {
-#pragma unroll
-    for (int cpt = 0; cpt < 4; ++cpt) {
-        float x = xs[m * kXS + i * 4 + cpt];
-        u[cpt] = normalise ? x / nrm[cpt * 32 + m] : x;
-    }
-}
-
-// forward encoder for pose `m` (one lane per pose); writes features as rows [i*6+o][m] of `feat`.
-__device__ __forceinline__ void encoder_forward(const float* encw, const float* xs, const float* nrm, float* feat, int m,
-                                                const KParams& p) {
+// forward encoder for this lane's pose; features are written as rows [i*6+o][m] of `feat`.
+__device__ __forceinline__ void encoder_forward(const float* encw, const float* xs, const float* nrm, float* feat,
+                                                const EncLane& e, const KParams& p) {
     for (int i = 0; i < 21; ++i) {
         const int par = c_parent[i];
-        float u[10], h[10], f[6], d1[10], d2[6];
-        load_q(xs, nrm, m, i, p.normalise != 0, u);
-        if (par >= 0) {
-#pragma unroll
-            for (int r = 0; r < 6; ++r) u[4 + r] = feat[swz(par * 6 + r, m)];
-        }
-        bone_mlp<false>(encw + enc_off(i), par < 0, u, p.enc_act, p.enc_beta, h, f, d1, d2);
-#pragma unroll
-        for (int o = 0; o < 6; ++o) feat[swz(i * 6 + o, m)] = f[o];
+        float u[10], h[10], f, d1a, d1b, d2;
+        bone_forward(encw + enc_off(i), par < 0, xs, nrm, feat, i, par, e, p, u, h, f, d1a, d1b, d2);
+        if (e.l < 6) feat[swz(i * 6 + e.l, e.m)] = f;
+        __syncwarp();
     }
 }
 
-// reverse encoder for pose `m`: features in `feat` (recomputed), feature gradients in rows [0,126) of
-// `gbuf` (accumulated in place), quaternion gradients written to rows [128+e] of `gbuf`.
+// reverse encoder: features in `feat` (recomputed), feature gradients in rows [0,126) of `gbuf` (accumulated in
+// place, reverse joint order is a reverse topological order), quaternion gradients -> rows [128+e] of `gbuf`.
 __device__ __forceinline__ void encoder_backward(const float* encw, const float* xs, const float* nrm, const float* feat,
-                                                 float* gbuf, int m, const KParams& p) {
+                                                 float* gbuf, const EncLane& e, const KParams& p) {
     for (int i = 20; i >= 0; --i) {
         const int par = c_parent[i];
         const bool root = par < 0;
-        float u[10], h[10], f[6], d1[10], d2[6];
-        load_q(xs, nrm, m, i, p.normalise != 0, u);
-        if (!root) {
-#pragma unroll
-            for (int r = 0; r < 6; ++r) u[4 + r] = feat[swz(par * 6 + r, m)];
-        }
-        const float* w = encw + enc_off(i);
-        bone_mlp<true>(w, root, u, p.enc_act, p.enc_beta, h, f, d1, d2);
         const int fin = root ? 4 : 10;
+        const float* w = encw + enc_off(i);
+        float u[10], h[10], f, d1a, d1b, d2;
+        bone_forward(w, root, xs, nrm, feat, i, par, e, p, u, h, f, d1a, d1b, d2);
         const float* w1 = w;
         const float* w2 = w + 10 * fin + 10;
+        // t[o] = fbar[o] * act'(pre2[o]) on lane o (< 6)
+        const float tl = (e.l < 6) ? gbuf[swz(i * 6 + e.l, e.m)] * d2 : 0.0f;
         float t[6];
 #pragma unroll
-        for (int o = 0; o < 6; ++o) t[o] = gbuf[swz(i * 6 + o, m)] * d2[o];
+        for (int o = 0; o < 6; ++o) t[o] = grp_get(tl, o, e);
+        // s1[k] = (sum_o t[o] W2[o][k]) * act'(pre1[k]) for this lane's hidden units k = l, 8+l
+        const int ka = e.l, kb = min(8 + e.l, 9);
+        float ga = 0.0f, gb = 0.0f;
+#pragma unroll
+        for (int o = 0; o < 6; ++o) {
+            ga = fmaf(t[o], w2[o * 10 + ka], ga);
+            gb = fmaf(t[o], w2[o * 10 + kb], gb);
+        }
+        ga *= d1a;
+        gb *= d1b;
         float s1[10];
 #pragma unroll
+        for (int k = 0; k < 8; ++k) s1[k] = grp_get(ga, k, e);
+        s1[8] = grp_get(gb, 0, e);
+        s1[9] = grp_get(gb, 1, e);
+        // ubar[j] = sum_k s1[k] W1[k][j] for this lane's inputs j = l (and 8+l for l < 2, non-root)
+        const int ja = root ? min(e.l, 3) : e.l, jb = min(8 + e.l, 9);
+        float ua = 0.0f, ub = 0.0f;
+#pragma unroll
         for (int k = 0; k < 10; ++k) {
-            float s = 0.0f;
-#pragma unroll
-            for (int o = 0; o < 6; ++o) s = fmaf(t[o], w2[o * 10 + k], s);
-            s1[k] = s * d1[k];
+            ua = fmaf(s1[k], w1[k * fin + ja], ua);
+            if (!root) ub = fmaf(s1[k], w1[k * fin + jb], ub);
         }
-        if (root) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float s = 0.0f;
-#pragma unroll
-                for (int k = 0; k < 10; ++k) s = fmaf(s1[k], w1[k * 4 + j], s);
-                gbuf[swz(128 + i * 4 + j, m)] = s;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                float s = 0.0f;
-#pragma unroll
-                for (int k = 0; k < 10; ++k) s = fmaf(s1[k], w1[k * 10 + j], s);
-                if (j < 4)
-                    gbuf[swz(128 + i * 4 + j, m)] = s;
-                else
-                    gbuf[swz(par * 6 + (j - 4), m)] += s;
-            }
+        if (e.l < 4) {
+            gbuf[swz(128 + i * 4 + e.l, e.m)] = ua;
+        } else if (!root) {
+            gbuf[swz(par * 6 + (e.l - 4), e.m)] += ua;
         }
+        if (!root && e.l < 2) gbuf[swz(par * 6 + 4 + e.l, e.m)] += ub;
+        __syncwarp();
     }
 }
 
@@ -573,6 +600,8 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     c.df_act = p.df_act; c.df_beta = p.df_beta;
     c.dscr = p.dscratch ? p.dscratch + (size_t)blockIdx.x * kUnits * 32 : nullptr;
     const bool keep = kGrad;
+    EncLane enc;
+    enc.l = lane & 7; enc.base = lane & 24; enc.m = warp * 4 + (lane >> 3);
     Pipe pipe;
     pipe.stage = 0; pipe.phase = 0; pipe.g = 0;
     pipe.step_slabs = (uint32_t)step_slabs;
@@ -621,32 +650,30 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
 
         for (int st = 0; st < p.steps; ++st) {
             float* dbg_s = (st == 0) ? dbg : nullptr;
-            // ---- column norms + encoder (one lane per pose)
-            if (warp == 0) {
-                const int m = lane;
+            // ---- column norms + encoder: 8 lanes per pose, 4 poses per warp
+            {
+                const int cpt = enc.l & 3, hf = enc.l >> 2;
                 if (p.normalise) {
-#pragma unroll
-                    for (int cpt = 0; cpt < 4; ++cpt) {
-                        float s = 0.0f;
-                        for (int j = 0; j < 21; ++j) {
-                            const float x = xs[m * kXS + j * 4 + cpt];
-                            s = fmaf(x, x, s);
-                        }
-                        nrm[cpt * 32 + m] = fmaxf(sqrtf(s), 1e-12f);
+                    float sq = 0.0f;
+                    for (int j = hf; j < 21; j += 2) {
+                        const float x = xs[enc.m * kXS + j * 4 + cpt];
+                        sq = fmaf(x, x, sq);
                     }
+                    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+                    if (hf == 0) nrm[cpt * 32 + enc.m] = fmaxf(sqrtf(sq), 1e-12f);
+                    __syncwarp();
                 }
                 if (p.use_enc) {
-                    encoder_forward(encw, xs, nrm, X, m, p);
-                    X[swz(126, m)] = 0.0f;
-                    X[swz(127, m)] = 0.0f;
+                    encoder_forward(encw, xs, nrm, X, enc, p);
+                    if (enc.l < 2) X[swz(126 + enc.l, enc.m)] = 0.0f;
                 } else {
-                    for (int e = 0; e < 96; ++e) {
+                    for (int e = enc.l; e < 96; e += 8) {
                         float v = 0.0f;
                         if (e < 84) {
-                            const float x = xs[m * kXS + e];
-                            v = p.normalise ? x / nrm[(e & 3) * 32 + m] : x;
+                            const float x = xs[enc.m * kXS + e];
+                            v = p.normalise ? x / nrm[(e & 3) * 32 + enc.m] : x;
                         }
-                        X[swz(e, m)] = v;
+                        X[swz(e, enc.m)] = v;
                     }
                 }
             }
@@ -703,18 +730,25 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             }
             gemm_bar();
             dump_rows(dbg_s, 2688, X, 64, tid);
-            // L6 (64 -> 1) + output activation: one lane per pose
-            if (warp == 0) {
-                const int m = lane;
-                float s = __ldg(p.bias[6]);
-                for (int k = 0; k < 64; ++k) s = fmaf(__ldg(p.w6 + k), X[swz(k, m)], s);
-                float dv;
-                const float d = act_eval(s, (p.df_act == ACT_SOFTPLUS) ? ACT_SOFTPLUS : ACT_RELU, p.df_beta, dv);
-                dval[m] = d;
-                float gu = 1.0f;
-                if (p.g_up != nullptr && m < nvalid) gu = __ldg(p.g_up + pose0 + m);
-                dval[32 + m] = gu * dv;
-                if (p.dist != nullptr && m < nvalid && st == p.steps - 1) p.dist[pose0 + m] = d;
+            // L6 (64 -> 1) + output activation: 8 lanes per pose, shuffle reduction
+            {
+                const int m = enc.m;
+                float s = 0.0f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s = fmaf(__ldg(p.w6 + enc.l + 8 * k), X[swz(enc.l + 8 * k, m)], s);
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s += __ldg(p.bias[6]);
+                if (enc.l == 0) {
+                    float dv;
+                    const float d = act_eval(s, (p.df_act == ACT_SOFTPLUS) ? ACT_SOFTPLUS : ACT_RELU, p.df_beta, dv);
+                    dval[m] = d;
+                    float gu = 1.0f;
+                    if (p.g_up != nullptr && m < nvalid) gu = __ldg(p.g_up + pose0 + m);
+                    dval[32 + m] = gu * dv;
+                    if (p.dist != nullptr && m < nvalid && st == p.steps - 1) p.dist[pose0 + m] = d;
+                }
             }
             if (!kGrad) {
                 gemm_bar();
@@ -787,42 +821,43 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             gemm_bar();
             dump_rows(dbg_s, 5376, Y, 128, tid);
 
-            // ---- encoder reverse + normalise Jacobian + step (one lane per pose)
-            if (warp == 0) {
-                const int m = lane;
+            // ---- encoder reverse + normalise Jacobian + step: 8 lanes per pose
+            {
+                const int m = enc.m;
                 if (p.use_enc) {
-                    encoder_forward(encw, xs, nrm, X, m, p);          // recompute features (X is free)
-                    encoder_backward(encw, xs, nrm, X, Y, m, p);      // qbar -> Y rows [128, 212)
+                    encoder_forward(encw, xs, nrm, X, enc, p);          // recompute features (X is free)
+                    encoder_backward(encw, xs, nrm, X, Y, enc, p);      // qbar -> Y rows [128, 212)
                 } else {
-                    for (int e = 0; e < 84; ++e) Y[swz(128 + e, m)] = Y[swz(e, m)];
+                    for (int e = enc.l; e < 84; e += 8) Y[swz(128 + e, m)] = Y[swz(e, m)];
+                    __syncwarp();
                 }
                 const float d = dval[m];
                 // xbar = (qbar - q <q,qbar>) / n   per component column  (Jacobian of F.normalize(dim=1))
-#pragma unroll
-                for (int cpt = 0; cpt < 4; ++cpt) {
-                    float n = 1.0f, dot = 0.0f;
-                    if (p.normalise) {
-                        n = nrm[cpt * 32 + m];
-                        for (int j = 0; j < 21; ++j) dot = fmaf(xs[m * kXS + j * 4 + cpt] / n, Y[swz(128 + j * 4 + cpt, m)], dot);
-                        if (n <= 1e-12f) dot = 0.0f;   // clamp active: map is x/eps, Jacobian is I/eps
-                    }
-                    for (int j = 0; j < 21; ++j) {
-                        const int e = j * 4 + cpt;
-                        const float x = xs[m * kXS + e];
-                        float g = Y[swz(128 + e, m)];
-                        if (p.normalise) g = (g - (x / n) * dot) / n;
-                        Y[swz(128 + e, m)] = g;
-                        if (p.do_step) xs[m * kXS + e] = __fsub_rn(x, __fmul_rn(d, g));   // two roundings, as torch's x - d*g
-                    }
+                const int cpt = enc.l & 3, hf = enc.l >> 2;
+                float n = 1.0f, dot = 0.0f;
+                if (p.normalise) {
+                    n = nrm[cpt * 32 + m];
+                    for (int j = hf; j < 21; j += 2) dot = fmaf(xs[m * kXS + j * 4 + cpt] / n, Y[swz(128 + j * 4 + cpt, m)], dot);
+                    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+                    if (n <= 1e-12f) dot = 0.0f;   // clamp active: map is x/eps, Jacobian is I/eps
+                }
+                for (int j = hf; j < 21; j += 2) {
+                    const int e = j * 4 + cpt;
+                    const float x = xs[m * kXS + e];
+                    float g = Y[swz(128 + e, m)];
+                    if (p.normalise) g = (g - (x / n) * dot) / n;
+                    Y[swz(128 + e, m)] = g;
+                    if (p.do_step) xs[m * kXS + e] = __fsub_rn(x, __fmul_rn(d, g));   // two roundings, as torch's x - d*g
                 }
                 if (p.do_step && p.renorm) {
-                    for (int j = 0; j < 21; ++j) {
-                        float s = 0.0f;
+                    __syncwarp();
+                    for (int j = enc.l; j < 21; j += 8) {
+                        float sq = 0.0f;
 #pragma unroll
-                        for (int cpt = 0; cpt < 4; ++cpt) s = fmaf(xs[m * kXS + j * 4 + cpt], xs[m * kXS + j * 4 + cpt], s);
-                        const float inv = 1.0f / sqrtf(s);
+                        for (int c4 = 0; c4 < 4; ++c4) sq = fmaf(xs[m * kXS + j * 4 + c4], xs[m * kXS + j * 4 + c4], sq);
+                        const float inv = 1.0f / sqrtf(sq);
 #pragma unroll
-                        for (int cpt = 0; cpt < 4; ++cpt) xs[m * kXS + j * 4 + cpt] *= inv;
+                        for (int c4 = 0; c4 < 4; ++c4) xs[m * kXS + j * 4 + c4] *= inv;
                     }
                 }
             }
