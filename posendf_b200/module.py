@@ -1,0 +1,231 @@
+"""Host-side mirror of the reference's call surface for the hot path: `PoseNDF(opt)`.
+
+Same constructor dict, same attributes (.enc, .dfnet, .device), same forward signature and return values,
+same 98 state_dict keys as /root/reference/model/posendf.py:30-101 -- so reference scripts
+(experiments/sample_poses.py:71,88-93, experiments/motion_denoise.py:82,125-130) and checkpoints keep
+working -- but `net(pose, train=False)` runs the fused sm_100a kernel through libpndf.so:
+
+  * pose does not require grad  -> one forward-only launch;
+  * pose requires grad          -> ONE launch computes dist and d(dist)/d(pose) analytically; backward()
+                                   / torch.autograd.grad(..., create_graph=True) just scale the stored
+                                   gradient by the upstream gradient (exact: dist[b] depends on pose[b] only).
+
+There is no CPU / eager fallback on this path: without libpndf.so or without a CUDA device it raises.
+
+The parameter-holding submodules (StructureEncoder / BoneMLP / DFNet) exist so that state_dict(),
+load_state_dict(), parameters() and .to() behave as in the reference; the packed device copy of the weights
+inside the engine is a cache that is rebuilt whenever a parameter tensor changes version.
+
+train=True (model/posendf.py:78-99: dist + manifold + Eikonal losses, needs d/dtheta and a double backward)
+is NOT part of the fused path yet; it is served by plain torch autograd over the same
+submodules on the GPU and documented as such in DESIGN.md.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .synth import PARENTS
+
+_BONE, _FEAT = 4, 6
+
+
+def _activation(kind: str, beta: float) -> nn.Module:
+    if kind == "relu":
+        return nn.ReLU()
+    if kind == "lrelu":
+        return nn.LeakyReLU()
+    if kind == "softplus":
+        return nn.Softplus(beta=beta)
+    raise ValueError(f"unknown activation {kind!r}")
+
+
+class BoneMLP(nn.Module):
+    """two-layer per-joint MLP; keys net.0 / net.2 (reference: model/network/net_modules.py:75-111)."""
+
+    def __init__(self, has_parent: bool, act: str, beta: float):
+        super().__init__()
+        hidden = _BONE + _FEAT
+        self.net = nn.Sequential(nn.Linear(hidden if has_parent else _BONE, hidden), _activation(act, beta),
+                                 nn.Linear(hidden, _FEAT), _activation(act, beta))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class StructureEncoder(nn.Module):
+    """21 bone MLPs walked along the kinematic tree (reference: model/network/net_modules.py:114-170)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.parent_mapping = list(PARENTS)
+        self.num_joints = len(self.parent_mapping)
+        self.out_dim = self.num_joints * _FEAT
+        self.net = nn.ModuleList(BoneMLP(p >= 0, opt["act"], opt["beta"]) for p in self.parent_mapping)
+
+    def get_out_dim(self):
+        return self.out_dim
+
+    def forward(self, quat):
+        feats = []
+        for i, mlp in enumerate(self.net):
+            p = self.parent_mapping[i]
+            feats.append(mlp(quat[:, i] if p < 0 else torch.cat((quat[:, i], feats[p]), dim=-1)))
+        return torch.cat(feats, dim=-1)
+
+
+class DFNet(nn.Module):
+    """distance head; keys lin{l} (reference: model/network/net_modules.py:9-72)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        widths = [opt["in_dim"], *opt["dims"], 1]
+        self.num_layers = len(widths)
+        for l in range(len(widths) - 1):
+            setattr(self, f"lin{l}", nn.Linear(widths[l], widths[l + 1]))
+        self.actv = _activation(opt["act"], opt["beta"])
+        self.out_actv = nn.Softplus(beta=opt["beta"]) if opt["act"] == "softplus" else nn.ReLU()
+
+    def forward(self, p):
+        x = p.reshape(len(p), -1)
+        last = self.num_layers - 2
+        for l in range(last + 1):
+            x = getattr(self, f"lin{l}")(x)
+            x = self.actv(x) if l < last else self.out_actv(x)
+        return x
+
+
+class _FusedDistance(torch.autograd.Function):
+    """dist = PoseNDF(pose) with the analytic input gradient computed in the same launch."""
+
+    @staticmethod
+    def forward(ctx, pose, engine, normalise):
+        dist, grad = engine.forward_grad(pose, normalise=normalise)
+        ctx.save_for_backward(grad)
+        ctx.pose_shape = pose.shape
+        return dist
+
+    @staticmethod
+    def backward(ctx, g_up):
+        (grad,) = ctx.saved_tensors
+        return (g_up.reshape(-1, 1, 1) * grad).reshape(ctx.pose_shape), None, None
+
+
+class PoseNDF(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.device = opt["train"]["device"]
+        m = opt["model"]
+        self.enc = StructureEncoder(m["StrEnc"]).to(self.device) if m["StrEnc"]["use"] else None
+        self.dfnet = DFNet(m["DFNet"]).to(self.device)
+        self.loss = opt["train"]["loss_type"]
+        self.batch_size = opt["train"]["batch_size"]
+        if self.loss == "l1":
+            self.loss_l1 = nn.L1Loss()
+        elif self.loss == "l2":
+            self.loss_l1 = nn.MSELoss()
+        self._cfg = dict(use_enc=bool(m["StrEnc"]["use"]), enc_act=m["StrEnc"].get("act", "lrelu"),
+                         enc_beta=float(m["StrEnc"].get("beta", 100.0)), df_act=m["DFNet"]["act"],
+                         df_beta=float(m["DFNet"].get("beta", 100.0)), in_dim=int(m["DFNet"]["in_dim"]),
+                         dims=tuple(int(d) for d in m["DFNet"]["dims"]))
+        self._engine = None
+        self._engine_key = None
+        self._weights_sig = None
+
+    # the reference's train() override returns None; returning self is a harmless superset
+    def train(self, mode=True):
+        super().train(mode)
+        return self
+
+    # ------------------------------------------------------------------ fused path plumbing
+    def _ordered_params(self):
+        out = []
+        if self.enc is not None:
+            for mlp in self.enc.net:
+                out += [mlp.net[0].weight, mlp.net[0].bias, mlp.net[2].weight, mlp.net[2].bias]
+        for l in range(self.dfnet.num_layers - 1):
+            lin = getattr(self.dfnet, f"lin{l}")
+            out += [lin.weight, lin.bias]
+        return out
+
+    def engine(self):
+        """libpndf handle on the device the parameters live on, with the current weights loaded."""
+        params = self._ordered_params()
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("posendf_b200.PoseNDF: the distance field runs only as the fused CUDA kernel "
+                               f"(parameters are on {dev}); there is no CPU fallback")
+        key = (dev.index if dev.index is not None else torch.cuda.current_device())
+        if self._engine is None or self._engine_key != key:
+            from .engine import Engine
+            c = self._cfg
+            self._engine = Engine(device=key, use_enc=c["use_enc"], enc_act=c["enc_act"], enc_beta=c["enc_beta"],
+                                  df_act=c["df_act"], df_beta=c["df_beta"], in_dim=c["in_dim"], dims=c["dims"])
+            self._engine_key = key
+            self._weights_sig = None
+        sig = tuple((p.data_ptr(), p._version) for p in params)
+        if sig != self._weights_sig:
+            flat = torch.cat([p.detach().reshape(-1).float() for p in params]).cpu().numpy()
+            self._engine.set_weights_flat(np.ascontiguousarray(flat))
+            self._weights_sig = sig
+        return self._engine
+
+    def distance(self, pose, normalise=True):
+        """(B,1) distances on the module's device; differentiable w.r.t. `pose` (first order)."""
+        eng = self.engine()
+        x = pose.to(device=eng.device).reshape(-1, 21, 4)
+        if x.dtype != torch.float32:
+            x = x.float()
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _FusedDistance.apply(x, eng, normalise)
+        return eng.forward(x, normalise=normalise)
+
+    @torch.no_grad()
+    def project(self, pose, steps=10, renorm=False):
+        """the loop of experiments/sample_poses.py:70-74 fused in one launch; returns (projected poses, dist of the
+        last evaluated step).  renorm=True re-normalises every quaternion after each step (north-star option)."""
+        eng = self.engine()
+        x = pose.detach().to(device=eng.device, dtype=torch.float32).reshape(-1, 21, 4).contiguous().clone()
+        dist = eng.project_(x, steps=steps, renorm=renorm)
+        return x, dist
+
+    @torch.no_grad()
+    def project_host(self, pose_cpu, steps=10, renorm=False):
+        """same, host tensors in / out through pndf_project_host (copies inside the library)."""
+        eng = self.engine()
+        x = pose_cpu.detach().to(dtype=torch.float32).reshape(-1, 21, 4).contiguous()
+        return eng.project_host(x, steps=steps, renorm=renorm)
+
+    def prior_grad(self, axis_angle, g_up=None):
+        """motion-denoise prior term (experiments/motion_denoise.py:81-83): dist(B,1) and g_up*ddist/d(axis-angle)."""
+        eng = self.engine()
+        return eng.prior_grad(axis_angle.to(device=eng.device), g_up=g_up)
+
+    # ------------------------------------------------------------------ reference call surface
+    def forward(self, pose, dist_gt=None, man_poses=None, train=True, eikonal=0.0):
+        if not train:
+            return {"dist_pred": self.distance(pose)}
+        return self._train_forward(pose, dist_gt, man_poses, eikonal)
+
+    def _train_forward(self, pose, dist_gt, man_poses, eikonal):
+        # torch autograd over the parameter submodules (cuBLAS), not the fused kernel: see module docstring
+        pose = pose.to(device=self.device).reshape(-1, 21, 4)
+        pose.requires_grad = True
+        dist_gt = dist_gt.to(device=self.device).reshape(-1)
+        q = nn.functional.normalize(pose, dim=1)
+        dist_pred = self.dfnet(self.enc(q) if self.enc is not None else q)
+        man = man_poses.to(device=self.device).reshape(-1, 21, 4)
+        dist_man = self.dfnet(self.enc(man) if self.enc is not None else man)
+        loss = self.loss_l1(dist_pred[:, 0], dist_gt)
+        if eikonal > 0.0:
+            (g,) = torch.autograd.grad(dist_pred, pose, torch.ones_like(dist_pred), create_graph=True, retain_graph=True)
+            eik = ((g.norm(2, dim=-1) - 1) ** 2).mean()
+            return loss, {"dist": loss, "man_loss": dist_man.abs().mean(), "eikonal": eik}
+        return loss, {"dist": loss}
+
+
+def gradient(inputs, outputs):
+    """the reference's helper (model/posendf.py:18-27): d(outputs)/d(inputs) with ones as upstream gradient."""
+    return torch.autograd.grad(outputs=outputs, inputs=inputs, grad_outputs=torch.ones_like(outputs),
+                               create_graph=True, retain_graph=True, only_inputs=True)[0]

@@ -216,3 +216,61 @@ def test_large_batch_properties():
     y = x.clone()
     eng.project_(y, steps=1)
     assert torch.equal(y, x - d.reshape(-1, 1, 1) * g)
+
+
+# ---------------------------------------------------------------------------- reference call surface on the GPU
+def _opt(meta):
+    cfg = case_cfg(meta)
+    return {"train": {"device": "cuda", "loss_type": meta.get("loss_type", "l1"), "batch_size": 4},
+            "model": {"StrEnc": {"use": cfg["use_enc"], "act": cfg["enc_act"], "beta": cfg["enc_beta"]},
+                      "DFNet": {"in_dim": 126 if cfg["use_enc"] else 84, "dims": [256, 512, 1024, 512, 256, 64],
+                                "act": cfg["df_act"], "beta": cfg["df_beta"]}}}
+
+
+@pytest.mark.parametrize("name", ["lrelu_enc_s1", "softplus_enc_s3", "lrelu_noenc_s6"])
+def test_module_drop_in_forward_and_autograd(name):
+    """the exact call pattern of experiments/sample_poses.py:66-74 against the reference's golden output."""
+    from posendf_b200 import PoseNDF, gradient
+    meta, z = load_golden(name)
+    params, poses = case_inputs(meta)
+    net = PoseNDF(_opt(meta))
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    net.eval()
+    noisy = torch.from_numpy(poses).cuda()
+    noisy.requires_grad = True
+    for _ in range(10):
+        pred = net(noisy, train=False)
+        grad = gradient(noisy, pred["dist_pred"]).reshape(-1, 84)
+        noisy = noisy - (pred["dist_pred"] * grad).reshape(-1, 21, 4)
+    assert_pose_parity(noisy.detach().cpu().numpy(), z["proj64"])
+    # fused K-step projection gives the same trajectory
+    x, d = net.project(torch.from_numpy(poses), steps=10)
+    assert_pose_parity(x.cpu().numpy(), z["proj64"])
+    assert np.max(per_pose_rel(x.cpu().numpy(), noisy.detach().cpu().numpy())) < 1e-6
+    # no-grad forward, any leading shape, CPU input moved like the reference's .to(device)
+    with torch.no_grad():
+        d0 = net(torch.from_numpy(poses).reshape(8, 8, 84), train=False)["dist_pred"]
+    assert d0.shape == (64, 1) and np.max(rel_err(d0.cpu().numpy(), z["d64"])) < 1e-5
+
+
+def test_module_backward_with_upstream_gradient_and_weight_refresh():
+    """motion_denoise-style: loss = w * mean(dist)^2 ; backward() reaches the pose through the fused gradient."""
+    from posendf_b200 import PoseNDF
+    meta, z = load_golden("lrelu_enc_s1")
+    cfg = case_cfg(meta)
+    params, poses = case_inputs(meta)
+    net = PoseNDF(_opt(meta))
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    x = torch.from_numpy(poses).cuda().requires_grad_(True)
+    d = net(x, train=False)["dist_pred"]
+    loss = 1e7 * torch.mean(d) ** 2
+    loss.backward()
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    dref, gref = onp.forward_grad(p64, poses.astype(np.float64), cfg)
+    up = 1e7 * 2 * dref.mean() / len(dref)
+    assert_grad_parity(x.grad.cpu().numpy(), up * gref)
+    # in-place weight update (an optimiser step) must invalidate the packed device copy
+    with torch.no_grad():
+        net.dfnet.lin6.bias.add_(0.25)
+    d2 = net(x.detach(), train=False)["dist_pred"]
+    assert torch.allclose(d2, d.detach() + 0.25, atol=1e-6)
