@@ -97,6 +97,19 @@ class ClockSampler:
         return out
 
 
+def host_threads():
+    """threads this process can really use: min(affinity mask, cgroup cpu quota) -- on the GPU box os.cpu_count()
+    says 128 while the container's cgroup grants 16 CPUs; oversubscribing them makes torch ~10x slower."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_reference_rate(batch, budget_s, threads):
     """oracle torch-CPU port of the reference step (forward, autograd gradient, x - d*g): best poses/s over as
     many repetitions of a `batch`-pose step as fit in ~budget_s seconds (at least 2, at most 8)."""
@@ -125,7 +138,7 @@ def run_reference(args, rank, world):
     travel to the GPU box) on all host threads, bounded sample per step."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     sample = 8192
     from oracle import posendf_torch as otorch
     from oracle.posendf_numpy import default_cfg
@@ -293,7 +306,7 @@ def main():
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = host_threads()
             cpu_rate, times = cpu_reference_rate(16384, 20.0, threads)
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{len(times)} x 16 384 poses of the same step (forward + autograd grad + x-d*g), "
