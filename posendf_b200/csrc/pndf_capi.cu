@@ -131,7 +131,7 @@ int pndf_create(const pndf_config* cfg, pndf_handle** out) {
     h->cfg = *cfg;
     h->num_sms = prop.multiProcessorCount;
     h->z0_rows = cfg->use_enc ? 128 : 96;
-    h->f0_slabs = h->z0_rows / 16;
+    h->f0_slabs = slabs_of(h->z0_rows, 256);
     CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
     CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
     if (cfg->df_act == PNDF_ACT_SOFTPLUS)
@@ -200,7 +200,8 @@ int pndf_set_weights(pndf_handle* h, const float* flat, size_t n) {
     pack_op(s, 512, 512, bwd(2, 512, 0));            // B2b
     pack_op(s, 512, 256, bwd(1, 0, 0));              // B1
     pack_op(s, 256, 128, bwd(0, 0, 0));              // B0 (in_dim padded to 128)
-    const size_t expect = (size_t)(h->f0_slabs + 32 + 256 + 32 + 4 + 4 + 32 + 256 + 32 + 8) * kSlabFloats;
+    const size_t expect = (size_t)(h->f0_slabs + 2 * slabs_of(256, 512) + 8 * slabs_of(512, 512) + 2 * slabs_of(512, 256) +
+                                   slabs_of(256, 64) + slabs_of(64, 256) + slabs_of(256, 128)) * kSlabFloats;
     if (s.size() != expect) return fail("internal: slab stream size mismatch");
     // ---- small parameters
     std::vector<float> sm;
@@ -336,8 +337,16 @@ namespace {
 
 template <int VARIANT>
 __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float seed) {
-    // 8x8 register tile like the GEMM inner loop: 64 independent accumulators, operands in registers
+    // 8x8 register tile like the GEMM inner loop: 64 independent accumulators.
+    // VARIANT 0: scalar FFMA, operands in registers      1: packed FFMA2 (fma.rn.f32x2)
+    //         2: half FFMA2 + half scalar FFMA           3: FFMA2 with the GEMM's shared-memory operand traffic
+    //            (4 LDS.128 per 32 FFMA2, broadcast pattern of the fused kernel)
+    __shared__ float4 sm[1152];
     float a[8], b[8], acc[8][8];
+    if (VARIANT == 3) {
+        for (int i = threadIdx.x; i < 1152; i += blockDim.x) sm[i] = make_float4(seed, -seed, 0.5f * seed, 0.25f * seed);
+        __syncthreads();
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         a[i] = seed + 0.001f * (threadIdx.x + i);
@@ -345,36 +354,92 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
     }
+    const int lane = threadIdx.x & 31, mg = lane >> 3, ngl = lane & 7, warp = threadIdx.x >> 5;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-      for (int rep = 0; rep < 4; ++rep) {
-        if (VARIANT == 0) {
+        for (int rep = 0; rep < 4; ++rep) {
+            if (VARIANT == 3) {
+                const int k = (it * 4 + rep) & 7;
+                const float4 a0 = sm[k * 8 + ((2 * mg) ^ k)], a1 = sm[k * 8 + ((2 * mg + 1) ^ k)];
+                const float4 b0 = sm[64 + k * 128 + warp * 8 + ngl], b1 = sm[64 + k * 128 + 64 + warp * 8 + ngl];
+                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+            }
+            if (VARIANT == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        } else {
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                unsigned long long aa;
-                asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a[i]));
+                for (int i = 0; i < 8; ++i) {
+                    unsigned long long aa;
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a[i]));
 #pragma unroll
-                for (int j = 0; j < 8; j += 2) {
-                    unsigned long long bb, cc;
-                    asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b[j]), "f"(b[j + 1]));
-                    asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(acc[i][j]), "f"(acc[i][j + 1]));
-                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cc) : "l"(aa), "l"(bb));
-                    asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][j]), "=f"(acc[i][j + 1]) : "l"(cc));
+                    for (int j = 0; j < 8; j += 2) {
+                        if (VARIANT == 2 && j >= 4) {
+                            acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                            acc[i][j + 1] = fmaf(a[i], b[j + 1], acc[i][j + 1]);
+                        } else {
+                            unsigned long long bb, cc;
+                            asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b[j]), "f"(b[j + 1]));
+                            asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(acc[i][j]), "f"(acc[i][j + 1]));
+                            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cc) : "l"(aa), "l"(bb));
+                            asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][j]), "=f"(acc[i][j + 1]) : "l"(cc));
+                        }
+                    }
                 }
             }
         }
-      }
     }
     float s = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += acc[i][j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// legacy warp-level tensor-core path (mma.sync) throughput probes: variant 10 = tf32 m16n8k8, 11 = bf16 m16n8k16.
+// 16 independent accumulator tiles per warp (32 poses x 64 features), fragments in registers.
+template <int VARIANT>
+__global__ void __launch_bounds__(256) mma_peak_kernel(float* out, int iters, float seed) {
+    float c[16][4];
+    unsigned a[2][4], b[8][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) a[i][r] = __float_as_uint(seed + 0.001f * (threadIdx.x + r + i));
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) b[j][r] = __float_as_uint(seed - 0.002f * (threadIdx.x + r + j));
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) c[t][r] = 0.0f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float* d = c[i * 8 + j];
+                if (VARIANT == 10) {
+                    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                                 : "r"(a[i][0]), "r"(a[i][1]), "r"(a[i][2]), "r"(a[i][3]), "r"(b[j][0]), "r"(b[j][1]));
+                } else {
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                                 : "r"(a[i][0]), "r"(a[i][1]), "r"(a[i][2]), "r"(a[i][3]), "r"(b[j][0]), "r"(b[j][1]));
+                }
+            }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) s += c[t][r];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
@@ -385,7 +450,7 @@ extern "C" int pndf_fp32_peak(int device, int variant, double* tflops) {
     CUDA_OK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 2048;
+    const int blocks = prop.multiProcessorCount * (variant == 3 ? 1 : 4), threads = 256, iters = (variant == 3 ? 8192 : 2048);
     float* out = nullptr;
     CUDA_OK(cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)));
     cudaEvent_t e0, e1;
@@ -394,16 +459,20 @@ extern "C" int pndf_fp32_peak(int device, int variant, double* tflops) {
     double best = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         CUDA_OK(cudaEventRecord(e0));
-        if (variant == 0)
-            fp32_peak_kernel<0><<<blocks, threads>>>(out, iters, 0.5f);
-        else
-            fp32_peak_kernel<1><<<blocks, threads>>>(out, iters, 0.5f);
+        if (variant == 0) fp32_peak_kernel<0><<<blocks, threads>>>(out, iters, 0.5f);
+        else if (variant == 1) fp32_peak_kernel<1><<<blocks, threads>>>(out, iters, 0.5f);
+        else if (variant == 2) fp32_peak_kernel<2><<<blocks, threads>>>(out, iters, 0.5f);
+        else if (variant == 3) fp32_peak_kernel<3><<<blocks, threads>>>(out, iters, 0.5f);
+        else if (variant == 10) mma_peak_kernel<10><<<blocks, threads>>>(out, iters, 0.5f);
+        else mma_peak_kernel<11><<<blocks, threads>>>(out, iters, 0.5f);
         CUDA_OK(cudaEventRecord(e1));
         CUDA_OK(cudaEventSynchronize(e1));
         CUDA_OK(cudaGetLastError());
         float ms = 0.0f;
         CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
-        const double flops = 2.0 * 64.0 * 4.0 * iters * (double)blocks * threads;
+        const double per_thread = (variant >= 10) ? 2.0 * 16.0 * (16 * 8 * (variant == 10 ? 8 : 16)) / 32.0 * iters
+                                                  : 2.0 * 64.0 * 4.0 * iters;
+        const double flops = per_thread * (double)blocks * threads;
         best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
     cudaEventDestroy(e0);

@@ -10,7 +10,7 @@
 //
 // The DFNet layers (99.8 % of the flops) run as register-tiled fp32 FFMA GEMMs: 256 compute threads, each
 // owning an 8-pose x TN-feature micro-tile; activations live in shared memory as [feature][pose] with a
-// 16-byte XOR swizzle; weights are streamed from L2 through a 3-stage ring of 16 KB slabs filled by a
+// 16-byte XOR swizzle; weights are streamed from L2 through a 4-stage ring of 16 KB slabs filled by a
 // rotating elected lane with cp.async.bulk (TMA 1-D bulk copies) + mbarriers.  The host pre-packs all
 // weights into ONE linear "slab stream" in exactly the order the tile consumes them (forward layout
 // W^T[k][n] for the forward ops, native W[out][in] for the reverse ops), so the producer just walks
@@ -29,11 +29,13 @@ constexpr int kGemmThreads = 256;     // 8 compute warps; the weight-slab produc
 constexpr int kThreads = 256;         // (256 threads -> 255 registers/thread for the 2x64 fused accumulators)
 constexpr int kSlabFloats = 4096;     // 16 KB weight slab = KC x N floats, KC*N == 4096
 constexpr int kSlabBytes = kSlabFloats * 4;
-constexpr int kStages = 3;
+constexpr int kStages = 4;
+__host__ __device__ constexpr int slabs_of(int K, int N) { return K * N / kSlabFloats; }
 constexpr int kXS = 85;               // padded row stride of the pose tile
 constexpr int kMaskStride = 2656;     // bytes per pose-group plane of the derivative bit masks
 constexpr int kUnits = 2624;          // hidden units of the DFNet (256+512+1024+512+256+64)
 constexpr int kEncFloats = 3516;
+constexpr int kEncStageRow = 256;     // encoder weights are parked in X rows [256, 366) while the encoder runs
 
 // unit offsets (mask / scratch index) of each hidden layer output z1..z6
 constexpr int kU1 = 0, kU2 = 256, kU3 = 768, kU4 = 1792, kU5 = 2304, kU6 = 2560;
@@ -43,8 +45,7 @@ constexpr int kSmX = 0;
 constexpr int kSmY = kSmX + 512 * 32 * 4;
 constexpr int kSmRing = kSmY + 512 * 32 * 4;
 constexpr int kSmMask = kSmRing + kStages * kSlabBytes;
-constexpr int kSmEncW = kSmMask + 4 * kMaskStride;
-constexpr int kSmXs = kSmEncW + 3520 * 4;
+constexpr int kSmXs = kSmMask + 4 * kMaskStride;
 constexpr int kSmNrm = kSmXs + kTileM * kXS * 4;
 constexpr int kSmDv = kSmNrm + 4 * 32 * 4;
 constexpr int kSmBar = kSmDv + 2 * 32 * 4;
@@ -201,80 +202,111 @@ __device__ __forceinline__ void acc_zero(float (&acc)[8][TN]) {
         for (int i = 0; i < 8; ++i) acc[i][j] = 0.0f;
 }
 
-// acc[8 poses][TN feats] += in[k][pose] * w[k][feat] over nslabs weight slabs (KC = 4096/(64*TN) rows each)
+// producer duty for slab g (rotates over the warps): refill the ring slot that slab g-1 occupied with slab
+// g + kStages - 1 of this CTA's stream.  Called by every thread (bookkeeping is replicated), acted on by one lane.
+__device__ __forceinline__ void producer_duty(Pipe& pipe, const Ctx& c) {
+    if (pipe.pf_left != 0) {
+        if ((pipe.g & 7u) == (uint32_t)(c.tid >> 5) && c.lane == 0) {
+            const uint32_t slot = (pipe.stage == 0) ? (kStages - 1) : (pipe.stage - 1);
+            if (pipe.g != 0) mbar_wait(&c.empty[slot], (pipe.stage == 0) ? (pipe.phase ^ 1u) : pipe.phase);
+            mbar_arrive_expect_tx(&c.full[slot], kSlabBytes);
+            bulk_g2s(const_cast<float*>(c.ring) + slot * kSlabFloats, pipe.wsrc + (size_t)pipe.pf_pos * kSlabBytes, kSlabBytes,
+                     &c.full[slot]);
+        }
+        --pipe.pf_left;
+        if (++pipe.pf_pos == pipe.step_slabs) pipe.pf_pos = 0;
+    }
+}
+
+template <int TN>
+struct Operands {
+    float a[8];
+    float b[TN];
+};
+
+// operands of one k-step: 8 pose values of this thread's pose group, TN weights of its feature group
+template <int TN>
+__device__ __forceinline__ void load_operands(Operands<TN>& o, const float* __restrict__ in, int k, const float* __restrict__ w,
+                                              int kk, const Ctx& c) {
+    constexpr int N = 64 * TN;
+    const int key = (k >> 2) & 7;
+    const float* row = in + k * 32;
+    const float4 a0 = *reinterpret_cast<const float4*>(row + (((c.mg * 2) ^ key) << 2));
+    const float4 a1 = *reinterpret_cast<const float4*>(row + (((c.mg * 2 + 1) ^ key) << 2));
+    o.a[0] = a0.x; o.a[1] = a0.y; o.a[2] = a0.z; o.a[3] = a0.w;
+    o.a[4] = a1.x; o.a[5] = a1.y; o.a[6] = a1.z; o.a[7] = a1.w;
+    if (TN == 8) {
+        const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + c.ng * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(w + kk * N + 256 + c.ng * 4);
+        o.b[0] = b0.x; o.b[1 % TN] = b0.y; o.b[2 % TN] = b0.z; o.b[3 % TN] = b0.w;
+        o.b[4 % TN] = b1.x; o.b[5 % TN] = b1.y; o.b[6 % TN] = b1.z; o.b[7 % TN] = b1.w;
+    } else if (TN == 4) {
+        const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + c.ng * 4);
+        o.b[0] = b0.x; o.b[1 % TN] = b0.y; o.b[2 % TN] = b0.z; o.b[3 % TN] = b0.w;
+    } else if (TN == 2) {
+        const float2 b0 = *reinterpret_cast<const float2*>(w + kk * N + c.ng * 2);
+        o.b[0] = b0.x; o.b[1 % TN] = b0.y;
+    } else {
+        o.b[0] = w[kk * N + c.ng];
+    }
+}
+
+template <int TN>
+__device__ __forceinline__ void fma_step(float (&acc)[8][TN], const Operands<TN>& o) {
+    if (TN >= 2) {
+        // packed fp32x2 FMA (Blackwell FFMA2): the pose value is the scalar-broadcast operand, two adjacent
+        // features ride in one 64-bit register pair -> half the issue slots of scalar FFMA, same rounding.
+        unsigned long long bb[(TN + 1) / 2];
+#pragma unroll
+        for (int j = 0; j < TN / 2; ++j) asm("mov.b64 %0, {%1, %2};" : "=l"(bb[j]) : "f"(o.b[2 * j]), "f"(o.b[(2 * j + 1) % TN]));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            unsigned long long aa;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(o.a[i]));
+#pragma unroll
+            for (int j = 0; j < TN / 2; ++j) {
+                unsigned long long cc;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(acc[i][2 * j]), "f"(acc[i][(2 * j + 1) % TN]));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cc) : "l"(aa), "l"(bb[j]));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2 * j]), "=f"(acc[i][(2 * j + 1) % TN]) : "l"(cc));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(o.a[i], o.b[j], acc[i][j]);
+    }
+}
+
+// acc[8 poses][TN feats] += in[k][pose] * w[k][feat] over nslabs weight slabs (KC = kSlabFloats/(64*TN) rows each).
+// The slab body is straight-line code (KC k-steps fully unrolled, ptxas software-pipelines the LDS under the
+// FFMA2s); the only scheduling barriers are the mbarrier wait at the top and the arrive at the bottom, so slabs
+// are made as large as shared memory allows (32 KB -> 1 boundary per 4096 packed FMAs per thread).
 template <int TN>
 __device__ __forceinline__ void gemm_op(float (&acc)[8][TN], const float* __restrict__ in, int nslabs, Pipe& pipe,
                                         const Ctx& c) {
     constexpr int N = 64 * TN;
     constexpr int KC = kSlabFloats / N;
-    const int mg2 = c.mg * 2;
+    producer_duty(pipe, c);
+    bool ready = mbar_try_wait(&c.full[pipe.stage], pipe.phase);
     for (int s = 0; s < nslabs; ++s) {
-        // producer duty (rotates over the warps): refill the slot freed by slab g-1 with slab g+kStages-1
-        if (pipe.pf_left != 0) {
-            if (c.lane == 0 && (pipe.g & 7u) == (uint32_t)(c.tid >> 5)) {
-                const uint32_t slot = (pipe.stage == 0) ? (kStages - 1) : (pipe.stage - 1);
-                if (pipe.g != 0) mbar_wait(&c.empty[slot], (pipe.stage == 0) ? (pipe.phase ^ 1u) : pipe.phase);
-                mbar_arrive_expect_tx(&c.full[slot], kSlabBytes);
-                bulk_g2s(const_cast<float*>(c.ring) + slot * kSlabFloats, pipe.wsrc + (size_t)pipe.pf_pos * kSlabBytes, kSlabBytes,
-                         &c.full[slot]);
-            }
-            --pipe.pf_left;
-            if (++pipe.pf_pos == pipe.step_slabs) pipe.pf_pos = 0;
-        }
-        mbar_wait(&c.full[pipe.stage], pipe.phase);
+        if (!ready) mbar_wait(&c.full[pipe.stage], pipe.phase);
         const float* __restrict__ w = c.ring + pipe.stage * kSlabFloats;
-        const float* __restrict__ rowbase = in + (s * KC) * 32;
-        const int kb = ((s * KC) >> 2) & 7;
-#pragma unroll
+        const uint32_t nstage = (pipe.stage + 1 == kStages) ? 0u : pipe.stage + 1;
+        const uint32_t nphase = (pipe.stage + 1 == kStages) ? (pipe.phase ^ 1u) : pipe.phase;
+#pragma unroll (KC > 32 ? 32 : KC)
         for (int kk = 0; kk < KC; ++kk) {
-            const int key = (kb + (kk >> 2)) & 7;
-            const float* row = rowbase + kk * 32;
-            const float4 a0 = *reinterpret_cast<const float4*>(row + (((mg2) ^ key) << 2));
-            const float4 a1 = *reinterpret_cast<const float4*>(row + (((mg2 + 1) ^ key) << 2));
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            float b[TN];
-            if (TN == 8) {
-                const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + c.ng * 4);
-                const float4 b1 = *reinterpret_cast<const float4*>(w + kk * N + 256 + c.ng * 4);
-                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
-                b[4 % TN] = b1.x; b[5 % TN] = b1.y; b[6 % TN] = b1.z; b[7 % TN] = b1.w;
-            } else if (TN == 4) {
-                const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + c.ng * 4);
-                b[0] = b0.x; b[1 % TN] = b0.y; b[2 % TN] = b0.z; b[3 % TN] = b0.w;
-            } else if (TN == 2) {
-                const float2 b0 = *reinterpret_cast<const float2*>(w + kk * N + c.ng * 2);
-                b[0] = b0.x; b[1 % TN] = b0.y;
-            } else {
-                b[0] = w[kk * N + c.ng];
-            }
-            if (TN >= 2) {
-                // packed fp32x2 FMA (Blackwell FFMA2): the pose value is the scalar-broadcast operand, two adjacent
-                // features ride in one 64-bit register pair -> half the issue slots of scalar FFMA, same rounding.
-                unsigned long long bb[(TN + 1) / 2];
-#pragma unroll
-                for (int j = 0; j < TN / 2; ++j) asm("mov.b64 %0, {%1, %2};" : "=l"(bb[j]) : "f"(b[2 * j]), "f"(b[(2 * j + 1) % TN]));
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    unsigned long long aa;
-                    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a[i]));
-#pragma unroll
-                    for (int j = 0; j < TN / 2; ++j) {
-                        unsigned long long cc;
-                        asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(acc[i][2 * j]), "f"(acc[i][(2 * j + 1) % TN]));
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cc) : "l"(aa), "l"(bb[j]));
-                        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][2 * j]), "=f"(acc[i][(2 * j + 1) % TN]) : "l"(cc));
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-            }
+            // probe the NEXT slab's barrier early: the ~90-cycle mbarrier round trip hides under this slab's FMAs
+            if (kk == (KC > 8 ? 4 : KC / 2)) ready = mbar_try_wait(&c.full[nstage], nphase);
+            Operands<TN> o;
+            load_operands<TN>(o, in, s * KC + kk, w, kk, c);
+            fma_step<TN>(acc, o);
         }
         __syncwarp();
         if (c.lane == 0) mbar_arrive(&c.empty[pipe.stage]);
         pipe.advance();
+        if (s + 1 < nslabs) producer_duty(pipe, c);
     }
 }
 
@@ -565,7 +597,8 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     float* Y = reinterpret_cast<float*>(smem + kSmY);
     float* ring = reinterpret_cast<float*>(smem + kSmRing);
     uint8_t* mask = smem + kSmMask;
-    float* encw = reinterpret_cast<float*>(smem + kSmEncW);
+    // encoder weights (14 KB) are staged into the idle upper half of X around the encoder phases only
+    float* encw = X + kEncStageRow * 32;
     float* xs = reinterpret_cast<float*>(smem + kSmXs);
     float* nrm = reinterpret_cast<float*>(smem + kSmNrm);
     float* dval = reinterpret_cast<float*>(smem + kSmDv);   // [32] distance, [32] upstream*out_act'
@@ -582,15 +615,14 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (p.use_enc) {
-        for (int i = tid; i < kEncFloats; i += kThreads) encw[i] = __ldg(p.encw + i);
-    }
     __syncthreads();
 
     // forward ops: F0(f0_slabs) F1(32) [F2a(64) F3a(64) F2b(64) F3b(64)] F4(32) F5(4)
     // reverse ops: B5(4) B4(32) [B3a(64) B2a(64) B3b(64) B2b(64)] B1(32) B0(8)
-    const int fwd_slabs = p.f0_slabs + 32 + 256 + 32 + 4;
-    const int bwd_slabs = 4 + 32 + 256 + 32 + 8;
+    constexpr int kS1 = slabs_of(256, 512), kS23 = slabs_of(512, 512), kS4 = slabs_of(512, 256), kS5 = slabs_of(256, 64);
+    constexpr int kSB5 = slabs_of(64, 256), kSB0 = slabs_of(256, 128);
+    const int fwd_slabs = p.f0_slabs + kS1 + 4 * kS23 + kS4 + kS5;
+    constexpr int bwd_slabs = kSB5 + kS1 + 4 * kS23 + kS4 + kSB0;
     const int step_slabs = fwd_slabs + (kGrad ? bwd_slabs : 0);
 
     // ------------------------------------------------------------------ compute warps
@@ -646,6 +678,9 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 for (int cpt = 0; cpt < 4; ++cpt) xs[m * kXS + j * 4 + cpt] = (m < nvalid) ? q[cpt] : 0.0f;
             }
         }
+        if (p.use_enc) {
+            for (int i = tid; i < kEncFloats; i += kGemmThreads) encw[i] = __ldg(p.encw + i);
+        }
         gemm_bar();
 
         for (int st = 0; st < p.steps; ++st) {
@@ -692,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             {   // F1: z1 (Y) -> z2 (X), 512 wide
                 float acc[8][8];
                 acc_init_bias<8>(acc, p.bias[1], c.ng, 512);
-                gemm_op<8>(acc, Y, 32, pipe, c);
+                gemm_op<8>(acc, Y, kS1, pipe, c);
                 epilogue_fwd<8>(acc, X, kU2, c, keep);
             }
             gemm_bar();
@@ -703,11 +738,11 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 for (int ch = 0; ch < 2; ++ch) {
                     float acc2[8][8];
                     acc_init_bias<8>(acc2, p.bias[2] + ch * 512, c.ng, 512);
-                    gemm_op<8>(acc2, X, 64, pipe, c);
+                    gemm_op<8>(acc2, X, kS23, pipe, c);
                     epilogue_fwd<8>(acc2, Y, kU3 + ch * 512, c, keep);
                     gemm_bar();
                     dump_rows(dbg_s, 896 + ch * 512, Y, 512, tid);
-                    gemm_op<8>(acc3, Y, 64, pipe, c);
+                    gemm_op<8>(acc3, Y, kS23, pipe, c);
                     gemm_bar();
                 }
                 epilogue_fwd<8>(acc3, X, kU4, c, keep);
@@ -717,7 +752,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             {   // F4: z4 (X) -> z5 (Y), 256 wide
                 float acc[8][4];
                 acc_init_bias<4>(acc, p.bias[4], c.ng, 256);
-                gemm_op<4>(acc, X, 32, pipe, c);
+                gemm_op<4>(acc, X, kS4, pipe, c);
                 epilogue_fwd<4>(acc, Y, kU5, c, keep);
             }
             gemm_bar();
@@ -725,7 +760,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             {   // F5: z5 (Y) -> z6 (X), 64 wide
                 float acc[8][1];
                 acc_init_bias<1>(acc, p.bias[5], c.ng, 64);
-                gemm_op<1>(acc, Y, 4, pipe, c);
+                gemm_op<1>(acc, Y, kS5, pipe, c);
                 epilogue_fwd<1>(acc, X, kU6, c, keep);
             }
             gemm_bar();
@@ -774,7 +809,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             {   // B5: g6 (Y,64) -> g5 (X,256)
                 float acc[8][4];
                 acc_zero<4>(acc);
-                gemm_op<4>(acc, Y, 4, pipe, c);
+                gemm_op<4>(acc, Y, kSB5, pipe, c);
                 epilogue_bwd<4>(acc, X, kU5, c);
             }
             gemm_bar();
@@ -782,7 +817,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             {   // B4: g5 (X,256) -> g4 (Y,512)
                 float acc[8][8];
                 acc_zero<8>(acc);
-                gemm_op<8>(acc, X, 32, pipe, c);
+                gemm_op<8>(acc, X, kS1, pipe, c);
                 epilogue_bwd<8>(acc, Y, kU4, c);
             }
             gemm_bar();
@@ -793,11 +828,11 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 for (int ch = 0; ch < 2; ++ch) {
                     float accb3[8][8];
                     acc_zero<8>(accb3);
-                    gemm_op<8>(accb3, Y, 64, pipe, c);
+                    gemm_op<8>(accb3, Y, kS23, pipe, c);
                     epilogue_bwd<8>(accb3, X, kU3 + ch * 512, c);
                     gemm_bar();
                     dump_rows(dbg_s, 3584 + ch * 512, X, 512, tid);
-                    gemm_op<8>(accb2, X, 64, pipe, c);
+                    gemm_op<8>(accb2, X, kS23, pipe, c);
                     gemm_bar();
                 }
                 epilogue_bwd<8>(accb2, Y, kU2, c);
@@ -807,7 +842,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             {   // B1: g2 (Y,512) -> g1 (X,256)
                 float acc[8][4];
                 acc_zero<4>(acc);
-                gemm_op<4>(acc, Y, 32, pipe, c);
+                gemm_op<4>(acc, Y, kS4, pipe, c);
                 epilogue_bwd<4>(acc, X, kU1, c);
             }
             gemm_bar();
@@ -815,13 +850,17 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             {   // B0: g1 (X,256) -> g0 (Y,128)
                 float acc[8][2];
                 acc_zero<2>(acc);
-                gemm_op<2>(acc, X, 8, pipe, c);
+                gemm_op<2>(acc, X, kSB0, pipe, c);
                 epilogue_bwd<2>(acc, Y, -1, c);
             }
             gemm_bar();
             dump_rows(dbg_s, 5376, Y, 128, tid);
 
             // ---- encoder reverse + normalise Jacobian + step: 8 lanes per pose
+            if (p.use_enc) {   // X is free again: park the encoder weights in its upper half
+                for (int i = tid; i < kEncFloats; i += kGemmThreads) encw[i] = __ldg(p.encw + i);
+                gemm_bar();
+            }
             {
                 const int m = enc.m;
                 if (p.use_enc) {
