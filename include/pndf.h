@@ -96,6 +96,17 @@ int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out
 int pndf_prior_grad(pndf_handle* h, const float* aa_dev, int64_t B, const float* g_up_dev, float* dist_dev,
                     float* grad_aa_dev, void* stream);
 
+/* Motion-denoise inner loop restricted to the prior term (experiments/motion_denoise.py:70,74-83,97-99 with the
+ * weights of :29-35): for it in range(iterations): for i in range(steps_per_iter):
+ *     loss_s = 1e7/(1+it) * mean_t(dist[s,t])^2  per sequence s;  backward to the axis-angle pose;  Adam(lr) step.
+ * aa_dev: S*T*63 floats, updated in place (S sequences of T frames, 21 joints x 3).  dist_dev (S*T, may be NULL):
+ * distances of the last evaluated step.  loss_hist_dev (iterations*steps_per_iter*S floats, may be NULL): the
+ * weighted prior loss per step and sequence.  Two launches per step: the fused prior kernel and a per-sequence
+ * mean + Adam kernel; everything stays on `stream`.  The SMPL temporal / data terms need licensed SMPL files and
+ * are out of scope. */
+int pndf_denoise_prior(pndf_handle* h, float* aa_dev, int64_t S, int64_t T, int iterations, int steps_per_iter, float lr,
+                       float* dist_dev, float* loss_hist_dev, void* stream);
+
 /* Debug / test hook: like pndf_forward_grad for the first 32 poses only, additionally dumping every
  * intermediate activation / gradient tile (layout documented in DESIGN.md) to dump_dev (floats). */
 int pndf_debug_dump_floats(size_t* n);

@@ -260,3 +260,31 @@ def train_losses(params, pose, dist_gt, man_poses, cfg, loss_type="l1", eikonal=
         gn = np.sqrt(np.sum(g * g, axis=-1))
         out["eikonal"] = ((gn - 1) ** 2).mean()
     return loss, out
+
+
+def denoise_prior(params, aa, cfg, iterations=10, steps_per_iter=50, lr=0.02, betas=(0.9, 0.999), eps=1e-8):
+    """experiments/motion_denoise.py:70,74-83,97-99 restricted to the prior term: for every sequence s
+    (aa: (S,T,21,3)) Adam(lr) on loss_s = 1e7/(1+it) * mean_t(dist)^2, torch.optim.Adam's update order."""
+    aa = np.array(aa, copy=True)
+    S, T = aa.shape[:2]
+    x = aa.reshape(S, T, 21, 3)
+    m = np.zeros_like(x); v = np.zeros_like(x)
+    hist = []
+    t = 0
+    d = None
+    for it in range(iterations):
+        w = 1e7 / (1.0 + it)
+        for _ in range(steps_per_iter):
+            t += 1
+            quat = axis_angle_to_quaternion(x.reshape(S * T, 21, 3))
+            d, qbar = forward_grad(params, quat, cfg)
+            graw = axis_angle_to_quaternion_vjp(x.reshape(S * T, 21, 3), qbar).reshape(S, T, 21, 3)
+            c = d.reshape(S, T).mean(axis=1)
+            hist.append(w * c * c)
+            g = (w * 2.0 * c / T).reshape(S, 1, 1, 1) * graw
+            m = betas[0] * m + (1 - betas[0]) * g
+            v = betas[1] * v + (1 - betas[1]) * g * g
+            step = lr / (1 - betas[0] ** t)
+            denom = np.sqrt(v) / np.sqrt(1 - betas[1] ** t) + eps
+            x = x - step * (m / denom)
+    return x, d.reshape(S, T), np.array(hist)

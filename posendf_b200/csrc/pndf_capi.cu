@@ -2,6 +2,7 @@
 // repacking of the reference state_dict into the kernel's slab stream, launches, host-buffer pipeline.
 #include "../../include/pndf.h"
 #include "pndf_kernel.cuh"
+#include "pndf_denoise.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -46,6 +47,9 @@ struct pndf_handle {
     float* d_chunk[2] = {nullptr, nullptr};
     float* d_chunk_dist[2] = {nullptr, nullptr};
     int64_t chunk_poses = 0;
+    // denoise loop state (pndf_denoise_prior): raw gradient, Adam moments, dist
+    float* d_dn[4] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t dn_poses = 0;
 };
 
 namespace {
@@ -146,6 +150,7 @@ int pndf_destroy(pndf_handle* h) {
     cudaFree(h->d_wstream);
     cudaFree(h->d_small);
     cudaFree(h->d_scratch);
+    for (int i = 0; i < 4; ++i) cudaFree(h->d_dn[i]);
     for (int i = 0; i < 2; ++i) {
         if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
         cudaFree(h->d_chunk[i]);
@@ -300,6 +305,53 @@ int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out
     }
     CUDA_OK(cudaStreamSynchronize(h->hs[0]));
     CUDA_OK(cudaStreamSynchronize(h->hs[1]));
+    return 0;
+}
+
+int pndf_denoise_prior(pndf_handle* h, float* aa_dev, int64_t S, int64_t T, int iterations, int steps_per_iter, float lr,
+                       float* dist_dev, float* loss_hist_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (S == 0 || T == 0) return 0;
+    if (S < 0 || T < 0 || !aa_dev) return fail("null argument");
+    if (iterations < 1 || steps_per_iter < 1) return fail("iterations and steps_per_iter must be >= 1");
+    if (T > (1 << 24) / 63) return fail("sequence too long");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t B = S * T;
+    if (h->dn_poses < B) {
+        for (int i = 0; i < 4; ++i) {
+            cudaFree(h->d_dn[i]);
+            h->d_dn[i] = nullptr;
+        }
+        for (int i = 0; i < 3; ++i) CUDA_OK(cudaMalloc(&h->d_dn[i], (size_t)B * 63 * sizeof(float)));
+        CUDA_OK(cudaMalloc(&h->d_dn[3], (size_t)B * sizeof(float)));
+        h->dn_poses = B;
+    }
+    float* graw = h->d_dn[0];
+    float* m = h->d_dn[1];
+    float* v = h->d_dn[2];
+    float* dist = dist_dev ? dist_dev : h->d_dn[3];
+    CUDA_OK(cudaMemsetAsync(m, 0, (size_t)B * 63 * sizeof(float), st));
+    CUDA_OK(cudaMemsetAsync(v, 0, (size_t)B * 63 * sizeof(float), st));
+    const double b1 = 0.9, b2 = 0.999;
+    double p1 = 1.0, p2 = 1.0;
+    int t = 0;
+    for (int it = 0; it < iterations; ++it) {
+        for (int i = 0; i < steps_per_iter; ++i, ++t) {
+            KParams p{};
+            p.pose_in = aa_dev; p.dist = dist; p.grad = graw; p.B = B; p.steps = 1; p.normalise = 1; p.input_kind = IN_AXIS_ANGLE;
+            if (launch(h, p, true, st)) return 1;
+            p1 *= b1; p2 *= b2;
+            AdamParams ap;
+            ap.lr = lr; ap.beta1 = (float)b1; ap.beta2 = (float)b2; ap.eps = 1e-8f;
+            ap.bias1 = (float)(1.0 - p1); ap.bias2 = (float)(1.0 - p2);
+            ap.weight = 1e7f / (1.0f + (float)it);
+            seq_adam_kernel<<<(unsigned)S, 256, 0, st>>>(aa_dev, graw, dist, m, v,
+                                                         loss_hist_dev ? loss_hist_dev + (size_t)t * S : nullptr, (int)T, ap);
+            CUDA_OK(cudaGetLastError());
+            h->launches++;
+        }
+    }
     return 0;
 }
 

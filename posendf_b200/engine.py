@@ -106,6 +106,19 @@ class Engine:
         _lib.check(self.lib.pndf_prior_grad(self._h, a.data_ptr(), B, gp, dist.data_ptr(), grad.data_ptr(), _stream_ptr(self.device)))
         return dist, grad
 
+    def denoise_prior_(self, aa, iterations=10, steps_per_iter=50, lr=0.02, want_loss=False):
+        """in place on a contiguous fp32 CUDA tensor (S,T,21,3) / (S,T,63); returns (dist (S,T), loss history or None)."""
+        if not (aa.is_cuda and aa.dtype == torch.float32 and aa.is_contiguous() and aa.device == self.device and aa.dim() >= 3):
+            raise RuntimeError("denoise_prior_ needs a contiguous fp32 CUDA tensor shaped (S, T, 63) or (S, T, 21, 3)")
+        S, T = aa.shape[0], aa.shape[1]
+        if aa.numel() != S * T * 63:
+            raise RuntimeError("denoise_prior_: last dims must hold 21 joints x 3")
+        dist = torch.empty(S, T, device=self.device, dtype=torch.float32)
+        hist = torch.empty(iterations * steps_per_iter, S, device=self.device, dtype=torch.float32) if want_loss else None
+        _lib.check(self.lib.pndf_denoise_prior(self._h, aa.data_ptr(), S, T, int(iterations), int(steps_per_iter), float(lr),
+                                               dist.data_ptr(), hist.data_ptr() if want_loss else None, _stream_ptr(self.device)))
+        return dist, hist
+
     def forward_grad_debug(self, pose, normalise=True):
         x = self._prep(pose, 84)
         B = min(x.shape[0], 32)

@@ -202,6 +202,18 @@ class PoseNDF(nn.Module):
         eng = self.engine()
         return eng.prior_grad(axis_angle.to(device=eng.device), g_up=g_up)
 
+    @torch.no_grad()
+    def denoise_prior(self, axis_angle, iterations=10, steps_per_iter=50, lr=0.02, want_loss=False):
+        """MotionDenoise.optimize restricted to the pose-prior term (experiments/motion_denoise.py:70-99): Adam on the
+        axis-angle poses of S sequences x T frames, loss_s = 1e7/(1+it) * mean_t(dist)^2.  Returns (poses, dist, losses)."""
+        eng = self.engine()
+        a = axis_angle.detach().to(device=eng.device, dtype=torch.float32)
+        if a.dim() == 2:
+            a = a.unsqueeze(0)
+        a = a.reshape(a.shape[0], a.shape[1], 63).contiguous().clone()
+        dist, hist = eng.denoise_prior_(a, iterations, steps_per_iter, lr, want_loss)
+        return a.reshape(a.shape[0], a.shape[1], 21, 3), dist, hist
+
     # ------------------------------------------------------------------ reference call surface
     def forward(self, pose, dist_gt=None, man_poses=None, train=True, eikonal=0.0):
         if not train:

@@ -139,3 +139,25 @@ def test_batch_permutation_and_nonnegativity():
     perm = np.random.default_rng(0).permutation(40)
     assert np.array_equal(onp.forward(params, x[perm], cfg), d[perm]) or np.allclose(onp.forward(params, x[perm], cfg), d[perm], rtol=1e-6)
     assert (d >= 0).all()
+
+
+def test_denoise_prior_oracle_matches_torch_adam_fp64():
+    """the numpy Adam loop of the oracle against torch.optim.Adam + autograd on the same prior loss."""
+    params = {k: v.astype(np.float64) for k, v in synth.make_params(1).items()}
+    cfg = onp.default_cfg()
+    aa = synth.make_axis_angle(5, 12, dtype=np.float64).reshape(2, 6, 21, 3)
+    x, d, h = onp.denoise_prior(params, aa, cfg, iterations=2, steps_per_iter=3)
+    tp = otorch.to_torch_params(params, torch.float64)
+    for s in range(2):
+        p = torch.from_numpy(aa[s].copy()).requires_grad_(True)
+        opt = torch.optim.Adam([p], 0.02, betas=(0.9, 0.999))
+        for it in range(2):
+            for _ in range(3):
+                opt.zero_grad()
+                ang = p.norm(dim=-1, keepdim=True)
+                q = torch.cat([torch.cos(ang / 2), p * torch.sin(ang / 2) / ang], dim=-1)
+                c = otorch.forward(tp, q, cfg).mean()
+                (1e7 * c * c / (1 + it)).backward()
+                opt.step()
+        assert np.max(np.abs(p.detach().numpy() - x[s])) < 1e-12
+    assert h.shape == (6, 2) and np.abs(x - aa).max() > 0.05
