@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
     //            (4 LDS.128 per 32 FFMA2, broadcast pattern of the fused kernel)
     __shared__ float4 sm[1152];
     float a[8], b[8], acc[8][8];
-    if (VARIANT == 3) {
+    if (VARIANT == 3 || VARIANT == 4) {
         for (int i = threadIdx.x; i < 1152; i += blockDim.x) sm[i] = make_float4(seed, -seed, 0.5f * seed, 0.25f * seed);
         __syncthreads();
     }
@@ -406,11 +406,12 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
     }
-    const int lane = threadIdx.x & 31, mg = lane >> 3, ngl = lane & 7, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int mg = (VARIANT == 4) ? (lane & 3) : (lane >> 3), ngl = (VARIANT == 4) ? (lane >> 2) : (lane & 7);
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int rep = 0; rep < 4; ++rep) {
-            if (VARIANT == 3) {
+            if (VARIANT == 3 || VARIANT == 4) {
                 const int k = (it * 4 + rep) & 7;
                 const float4 a0 = sm[k * 8 + ((2 * mg) ^ k)], a1 = sm[k * 8 + ((2 * mg + 1) ^ k)];
                 const float4 b0 = sm[64 + k * 128 + warp * 8 + ngl], b1 = sm[64 + k * 128 + 64 + warp * 8 + ngl];
@@ -502,7 +503,7 @@ extern "C" int pndf_fp32_peak(int device, int variant, double* tflops) {
     CUDA_OK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    const int blocks = prop.multiProcessorCount * (variant == 3 ? 1 : 4), threads = 256, iters = (variant == 3 ? 8192 : 2048);
+    const int blocks = prop.multiProcessorCount * ((variant == 3 || variant == 4) ? 1 : 4), threads = 256, iters = ((variant == 3 || variant == 4) ? 8192 : 2048);
     float* out = nullptr;
     CUDA_OK(cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)));
     cudaEvent_t e0, e1;
@@ -515,6 +516,7 @@ extern "C" int pndf_fp32_peak(int device, int variant, double* tflops) {
         else if (variant == 1) fp32_peak_kernel<1><<<blocks, threads>>>(out, iters, 0.5f);
         else if (variant == 2) fp32_peak_kernel<2><<<blocks, threads>>>(out, iters, 0.5f);
         else if (variant == 3) fp32_peak_kernel<3><<<blocks, threads>>>(out, iters, 0.5f);
+        else if (variant == 4) fp32_peak_kernel<4><<<blocks, threads>>>(out, iters, 0.5f);
         else if (variant == 10) mma_peak_kernel<10><<<blocks, threads>>>(out, iters, 0.5f);
         else mma_peak_kernel<11><<<blocks, threads>>>(out, iters, 0.5f);
         CUDA_OK(cudaEventRecord(e1));

@@ -172,23 +172,29 @@ struct Ctx {
     uint64_t* empty;
     float* dscr;   // this CTA's derivative scratch (softplus) or nullptr
     int tid, lane, mg, ng;
+    int ng2, kg;   // split-K ops (N = 256): feature group within a 4-warp K-group, and the K-group (0/1)
     int df_act;
     float df_beta;
 };
 
-template <int TN>
+// KG = number of K-groups an op is split into: KG == 1, all 8 warps tile N = 64*TN features; KG == 2 (split-K, used for
+// the 256-wide ops) two groups of 4 warps each tile the SAME N = 32*TN features over one half of every slab's rows.
+template <int KG>
+__device__ __forceinline__ int ngv(const Ctx& c) { return KG == 1 ? c.ng : c.ng2; }
+
+template <int TN, int KG = 1>
 __device__ __forceinline__ int feat_of(int ng, int j) {
-    if (TN == 8) return (j < 4) ? (ng * 4 + j) : (256 + ng * 4 + (j - 4));
+    if (TN == 8) return (j < 4) ? (ng * 4 + j) : (32 * TN / KG + ng * 4 + (j - 4));
     if (TN == 4) return ng * 4 + j;
     if (TN == 2) return ng * 2 + j;
     return ng;
 }
 
-template <int TN>
+template <int TN, int KG = 1>
 __device__ __forceinline__ void acc_init_bias(float (&acc)[8][TN], const float* __restrict__ bias, int ng, int nreal) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
-        int f = feat_of<TN>(ng, j);
+        int f = feat_of<TN, KG>(ng, j);
         float b = (f < nreal) ? __ldg(bias + f) : 0.0f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i][j] = b;
@@ -225,10 +231,11 @@ struct Operands {
 };
 
 // operands of one k-step: 8 pose values of this thread's pose group, TN weights of its feature group
-template <int TN>
+template <int TN, int KG = 1>
 __device__ __forceinline__ void load_operands(Operands<TN>& o, const float* __restrict__ in, int k, const float* __restrict__ w,
                                               int kk, const Ctx& c) {
-    constexpr int N = 64 * TN;
+    constexpr int N = 64 * TN / KG;
+    const int ng = ngv<KG>(c);
     const int key = (k >> 2) & 7;
     const float* row = in + k * 32;
     const float4 a0 = *reinterpret_cast<const float4*>(row + (((c.mg * 2) ^ key) << 2));
@@ -236,18 +243,18 @@ __device__ __forceinline__ void load_operands(Operands<TN>& o, const float* __re
     o.a[0] = a0.x; o.a[1] = a0.y; o.a[2] = a0.z; o.a[3] = a0.w;
     o.a[4] = a1.x; o.a[5] = a1.y; o.a[6] = a1.z; o.a[7] = a1.w;
     if (TN == 8) {
-        const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + c.ng * 4);
-        const float4 b1 = *reinterpret_cast<const float4*>(w + kk * N + 256 + c.ng * 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + ng * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(w + kk * N + N / 2 + ng * 4);
         o.b[0] = b0.x; o.b[1 % TN] = b0.y; o.b[2 % TN] = b0.z; o.b[3 % TN] = b0.w;
         o.b[4 % TN] = b1.x; o.b[5 % TN] = b1.y; o.b[6 % TN] = b1.z; o.b[7 % TN] = b1.w;
     } else if (TN == 4) {
-        const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + c.ng * 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + ng * 4);
         o.b[0] = b0.x; o.b[1 % TN] = b0.y; o.b[2 % TN] = b0.z; o.b[3 % TN] = b0.w;
     } else if (TN == 2) {
-        const float2 b0 = *reinterpret_cast<const float2*>(w + kk * N + c.ng * 2);
+        const float2 b0 = *reinterpret_cast<const float2*>(w + kk * N + ng * 2);
         o.b[0] = b0.x; o.b[1 % TN] = b0.y;
     } else {
-        o.b[0] = w[kk * N + c.ng];
+        o.b[0] = w[kk * N + ng];
     }
 }
 
@@ -283,11 +290,13 @@ __device__ __forceinline__ void fma_step(float (&acc)[8][TN], const Operands<TN>
 // The slab body is straight-line code (KC k-steps fully unrolled, ptxas software-pipelines the LDS under the
 // FFMA2s); the only scheduling barriers are the mbarrier wait at the top and the arrive at the bottom, so slabs
 // are made as large as shared memory allows (32 KB -> 1 boundary per 4096 packed FMAs per thread).
-template <int TN>
+template <int TN, int KG = 1>
 __device__ __forceinline__ void gemm_op(float (&acc)[8][TN], const float* __restrict__ in, int nslabs, Pipe& pipe,
                                         const Ctx& c) {
-    constexpr int N = 64 * TN;
-    constexpr int KC = kSlabFloats / N;
+    constexpr int N = 64 * TN / KG;
+    constexpr int KC = kSlabFloats / N;      // rows per slab
+    constexpr int KR = KC / KG;              // rows of each slab this thread's K-group consumes
+    const int k0 = (KG == 1) ? 0 : c.kg * KR;
     producer_duty(pipe, c);
     bool ready = mbar_try_wait(&c.full[pipe.stage], pipe.phase);
     for (int s = 0; s < nslabs; ++s) {
@@ -295,12 +304,12 @@ __device__ __forceinline__ void gemm_op(float (&acc)[8][TN], const float* __rest
         const float* __restrict__ w = c.ring + pipe.stage * kSlabFloats;
         const uint32_t nstage = (pipe.stage + 1 == kStages) ? 0u : pipe.stage + 1;
         const uint32_t nphase = (pipe.stage + 1 == kStages) ? (pipe.phase ^ 1u) : pipe.phase;
-#pragma unroll (KC > 32 ? 32 : KC)
-        for (int kk = 0; kk < KC; ++kk) {
+#pragma unroll (KR > 32 ? 32 : KR)
+        for (int kk = 0; kk < KR; ++kk) {
             // probe the NEXT slab's barrier early: the ~90-cycle mbarrier round trip hides under this slab's FMAs
-            if (kk == (KC > 8 ? 4 : KC / 2)) ready = mbar_try_wait(&c.full[nstage], nphase);
+            if (kk == (KR > 8 ? 4 : KR / 2)) ready = mbar_try_wait(&c.full[nstage], nphase);
             Operands<TN> o;
-            load_operands<TN>(o, in, s * KC + kk, w, kk, c);
+            load_operands<TN, KG>(o, in, s * KC + k0 + kk, w, k0 + kk, c);
             fma_step<TN>(acc, o);
         }
         __syncwarp();
@@ -318,7 +327,7 @@ __device__ __forceinline__ void store_row8(float* buf, int f, int mg, const floa
     *reinterpret_cast<float4*>(row + (((mg * 2 + 1) ^ key) << 2)) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
-template <int TN>
+template <int TN, int KG = 1>
 __device__ __forceinline__ void mask_store(uint8_t* mask, int mg, int unit0, const uint32_t (&bits)[TN]) {
     // units of one thread are consecutive in groups of min(TN,4)
     uint8_t* base = mask + mg * kMaskStride;
@@ -326,7 +335,7 @@ __device__ __forceinline__ void mask_store(uint8_t* mask, int mg, int unit0, con
 #pragma unroll
         for (int h = 0; h < TN / 4; ++h) {
             uint32_t wv = bits[h * 4] | (bits[h * 4 + 1] << 8) | (bits[h * 4 + 2] << 16) | (bits[h * 4 + 3] << 24);
-            *reinterpret_cast<uint32_t*>(base + unit0 + h * 256) = wv;
+            *reinterpret_cast<uint32_t*>(base + unit0 + h * (32 * TN / KG)) = wv;
         }
     } else if (TN == 2) {
         *reinterpret_cast<uint16_t*>(base + unit0) = (uint16_t)(bits[0] | (bits[1 % TN] << 8));
@@ -334,13 +343,13 @@ __device__ __forceinline__ void mask_store(uint8_t* mask, int mg, int unit0, con
         base[unit0] = (uint8_t)bits[0];
     }
 }
-template <int TN>
+template <int TN, int KG = 1>
 __device__ __forceinline__ void mask_load(const uint8_t* mask, int mg, int unit0, uint32_t (&bits)[TN]) {
     const uint8_t* base = mask + mg * kMaskStride;
     if (TN >= 4) {
 #pragma unroll
         for (int h = 0; h < TN / 4; ++h) {
-            uint32_t wv = *reinterpret_cast<const uint32_t*>(base + unit0 + h * 256);
+            uint32_t wv = *reinterpret_cast<const uint32_t*>(base + unit0 + h * (32 * TN / KG));
             bits[h * 4] = wv & 0xff; bits[h * 4 + 1] = (wv >> 8) & 0xff; bits[h * 4 + 2] = (wv >> 16) & 0xff; bits[h * 4 + 3] = wv >> 24;
         }
     } else if (TN == 2) {
@@ -353,13 +362,14 @@ __device__ __forceinline__ void mask_load(const uint8_t* mask, int mg, int unit0
 
 // forward epilogue: z = act(acc) (bias already in acc), remember the derivative, store z as next input.
 // unit_base: index of feature 0 of this op in the mask / scratch unit space.
-template <int TN>
+template <int TN, int KG = 1>
 __device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* out, int unit_base, const Ctx& c, bool keep_deriv) {
-    const int unit0 = unit_base + feat_of<TN>(c.ng, 0);
+    const int ng = ngv<KG>(c);
+    const int unit0 = unit_base + feat_of<TN, KG>(ng, 0);
     if (c.df_act == ACT_SOFTPLUS) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            const int f = feat_of<TN>(c.ng, j);
+            const int f = feat_of<TN, KG>(ng, j);
             float z[8], dv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) z[i] = act_eval(acc[i][j], ACT_SOFTPLUS, c.df_beta, dv[i]);
@@ -375,7 +385,7 @@ __device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* o
         uint32_t bits[TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            const int f = feat_of<TN>(c.ng, j);
+            const int f = feat_of<TN, KG>(ng, j);
             float z[8];
             uint32_t bm = 0;
 #pragma unroll
@@ -388,28 +398,29 @@ __device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* o
             bits[j] = bm;
             store_row8(out, f, c.mg, z);
         }
-        if (keep_deriv) mask_store<TN>(c.mask, c.mg, unit0, bits);
+        if (keep_deriv) mask_store<TN, KG>(c.mask, c.mg, unit0, bits);
     }
 }
 
 // reverse epilogue: g = acc * act'(pre) of the layer whose input-gradient this op produced; store as the
 // next reverse op's input.  unit_base < 0: no derivative (the encoder features, handled by the encoder).
-template <int TN>
+template <int TN, int KG = 1>
 __device__ __forceinline__ void epilogue_bwd(const float (&acc)[8][TN], float* out, int unit_base, const Ctx& c) {
+    const int ng = ngv<KG>(c);
     if (unit_base < 0) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = acc[i][j];
-            store_row8(out, feat_of<TN>(c.ng, j), c.mg, v);
+            store_row8(out, feat_of<TN, KG>(ng, j), c.mg, v);
         }
         return;
     }
     if (c.df_act == ACT_SOFTPLUS) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            const int f = feat_of<TN>(c.ng, j);
+            const int f = feat_of<TN, KG>(ng, j);
             const float* p = c.dscr + (size_t)(unit_base + f) * 32 + c.mg * 8;
             const float4 d0 = *reinterpret_cast<const float4*>(p);
             const float4 d1 = *reinterpret_cast<const float4*>(p + 4);
@@ -422,13 +433,41 @@ __device__ __forceinline__ void epilogue_bwd(const float (&acc)[8][TN], float* o
     } else {
         const float slope = (c.df_act == ACT_RELU) ? 0.0f : 0.01f;
         uint32_t bits[TN];
-        mask_load<TN>(c.mask, c.mg, unit_base + feat_of<TN>(c.ng, 0), bits);
+        mask_load<TN, KG>(c.mask, c.mg, unit_base + feat_of<TN, KG>(ng, 0), bits);
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = ((bits[j] >> i) & 1u) ? acc[i][j] : acc[i][j] * slope;
-            store_row8(out, feat_of<TN>(c.ng, j), c.mg, v);
+            store_row8(out, feat_of<TN, KG>(ng, j), c.mg, v);
+        }
+    }
+}
+
+// split-K ops: K-group 1 parks its partial sums in the op's output tile, K-group 0 adds them to its own and then
+// runs the epilogue over the same elements (same thread <-> element mapping in both groups).
+template <int TN>
+__device__ __forceinline__ void splitk_combine(float (&acc)[8][TN], float* out, const Ctx& c) {
+    if (c.kg == 1) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = acc[i][j];
+            store_row8(out, feat_of<TN, 2>(c.ng2, j), c.mg, v);
+        }
+    }
+    gemm_bar();
+    if (c.kg == 0) {
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int f = feat_of<TN, 2>(c.ng2, j);
+            const int key = (f >> 2) & 7;
+            const float* row = out + f * 32;
+            const float4 p0 = *reinterpret_cast<const float4*>(row + (((c.mg * 2) ^ key) << 2));
+            const float4 p1 = *reinterpret_cast<const float4*>(row + (((c.mg * 2 + 1) ^ key) << 2));
+            acc[0][j] += p0.x; acc[1][j] += p0.y; acc[2][j] += p0.z; acc[3][j] += p0.w;
+            acc[4][j] += p1.x; acc[5][j] += p1.y; acc[6][j] += p1.z; acc[7][j] += p1.w;
         }
     }
 }
@@ -629,6 +668,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     Ctx c;
     c.X = X; c.Y = Y; c.ring = ring; c.mask = mask; c.full = full; c.empty = empty;
     c.tid = tid; c.lane = lane; c.mg = lane >> 3; c.ng = warp * 8 + (lane & 7);
+    c.ng2 = (warp & 3) * 8 + (lane & 7); c.kg = warp >> 2;
     c.df_act = p.df_act; c.df_beta = p.df_beta;
     c.dscr = p.dscratch ? p.dscratch + (size_t)blockIdx.x * kUnits * 32 : nullptr;
     const bool keep = kGrad;
@@ -717,10 +757,11 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
 
             // ================================================================= forward
             {   // F0: z0 (X) -> z1 (Y), 256 wide
-                float acc[8][4];
-                acc_init_bias<4>(acc, p.bias[0], c.ng, 256);
-                gemm_op<4>(acc, X, p.f0_slabs, pipe, c);
-                epilogue_fwd<4>(acc, Y, kU1, c, keep);
+                float acc[8][8];
+                if (c.kg == 0) acc_init_bias<8, 2>(acc, p.bias[0], c.ng2, 256); else acc_zero<8>(acc);
+                gemm_op<8, 2>(acc, X, p.f0_slabs, pipe, c);
+                splitk_combine<8>(acc, Y, c);
+                if (c.kg == 0) epilogue_fwd<8, 2>(acc, Y, kU1, c, keep);
             }
             gemm_bar();
             dump_rows(dbg_s, 128, Y, 256, tid);
@@ -750,10 +791,11 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             gemm_bar();
             dump_rows(dbg_s, 1920, X, 512, tid);
             {   // F4: z4 (X) -> z5 (Y), 256 wide
-                float acc[8][4];
-                acc_init_bias<4>(acc, p.bias[4], c.ng, 256);
-                gemm_op<4>(acc, X, kS4, pipe, c);
-                epilogue_fwd<4>(acc, Y, kU5, c, keep);
+                float acc[8][8];
+                if (c.kg == 0) acc_init_bias<8, 2>(acc, p.bias[4], c.ng2, 256); else acc_zero<8>(acc);
+                gemm_op<8, 2>(acc, X, kS4, pipe, c);
+                splitk_combine<8>(acc, Y, c);
+                if (c.kg == 0) epilogue_fwd<8, 2>(acc, Y, kU5, c, keep);
             }
             gemm_bar();
             dump_rows(dbg_s, 2432, Y, 256, tid);
@@ -807,10 +849,11 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             gemm_bar();
             dump_rows(dbg_s, 2752, Y, 64, tid);
             {   // B5: g6 (Y,64) -> g5 (X,256)
-                float acc[8][4];
-                acc_zero<4>(acc);
-                gemm_op<4>(acc, Y, kSB5, pipe, c);
-                epilogue_bwd<4>(acc, X, kU5, c);
+                float acc[8][8];
+                acc_zero<8>(acc);
+                gemm_op<8, 2>(acc, Y, kSB5, pipe, c);
+                splitk_combine<8>(acc, X, c);
+                if (c.kg == 0) epilogue_bwd<8, 2>(acc, X, kU5, c);
             }
             gemm_bar();
             dump_rows(dbg_s, 2816, X, 256, tid);
@@ -840,10 +883,11 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             gemm_bar();
             dump_rows(dbg_s, 4608, Y, 512, tid);
             {   // B1: g2 (Y,512) -> g1 (X,256)
-                float acc[8][4];
-                acc_zero<4>(acc);
-                gemm_op<4>(acc, Y, kS4, pipe, c);
-                epilogue_bwd<4>(acc, X, kU1, c);
+                float acc[8][8];
+                acc_zero<8>(acc);
+                gemm_op<8, 2>(acc, Y, kS4, pipe, c);
+                splitk_combine<8>(acc, X, c);
+                if (c.kg == 0) epilogue_bwd<8, 2>(acc, X, kU1, c);
             }
             gemm_bar();
             dump_rows(dbg_s, 5120, X, 256, tid);
