@@ -77,13 +77,29 @@ size_t param_count(const pndf_config* c) {
     return n;
 }
 
-// Append one op's weights as slabs of KC rows x N floats.  get(k, n) returns w[k][n] (0 outside).
+// Append one op's weights in the per-warp slab order the kernel consumes (pndf_kernel.cuh): for each slab index,
+// for each of the 8 warps, R rows x FW feature columns (R*FW = 1024).  TN = features per thread, KG = K-groups.
+//   TN == 8: warp columns = [32 features starting at cg*32 | 32 features starting at N/2 + cg*32], cg = warp (KG 1) or
+//            warp & 3 (KG 2, N = 256; warps 4-7 hold the second half of the K rows)
+//   TN == 2: 16 features starting at warp*16;   TN == 1: 8 features starting at warp*8.
+// get(k, n) returns w[k][n] (0 outside the real matrix).
 template <class F>
-void pack_op(std::vector<float>& out, int K, int N, F get) {
-    const int KC = kSlabFloats / N;
-    for (int s = 0; s < K / KC; ++s)
-        for (int kk = 0; kk < KC; ++kk)
-            for (int n = 0; n < N; ++n) out.push_back(get(s * KC + kk, n));
+void pack_op(std::vector<float>& out, int K, int TN, int KG, F get) {
+    const int FW = 8 * TN, R = kSlabFloats / FW, N = 64 * TN / KG;
+    const int rows_per_group = K / KG, nslabs = rows_per_group / R;
+    for (int s = 0; s < nslabs; ++s)
+        for (int w = 0; w < kWarps; ++w) {
+            const int kg = (KG == 1) ? 0 : (w >> 2), cg = (KG == 1) ? w : (w & 3);
+            for (int r = 0; r < R; ++r) {
+                const int k = kg * rows_per_group + s * R + r;
+                for (int c = 0; c < FW; ++c) {
+                    int n;
+                    if (TN == 8) n = (c < 32) ? (cg * 32 + c) : (N / 2 + cg * 32 + (c - 32));
+                    else n = cg * FW + c;
+                    out.push_back(get(k, n));
+                }
+            }
+        }
 }
 
 int launch(pndf_handle* h, KParams& p, bool grad, cudaStream_t st) {
@@ -135,7 +151,7 @@ int pndf_create(const pndf_config* cfg, pndf_handle** out) {
     h->cfg = *cfg;
     h->num_sms = prop.multiProcessorCount;
     h->z0_rows = cfg->use_enc ? 128 : 96;
-    h->f0_slabs = slabs_of(h->z0_rows, 256);
+    h->f0_slabs = slabs_of(h->z0_rows, 2, 64);
     CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
     CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
     if (cfg->df_act == PNDF_ACT_SOFTPLUS)
@@ -180,7 +196,7 @@ int pndf_set_weights(pndf_handle* h, const float* flat, size_t n) {
     }
     // ---- slab stream, in consumption order (pndf_kernel.cuh)
     std::vector<float> s;
-    s.reserve((size_t)700 * kSlabFloats);
+    s.reserve((size_t)340 * kWarps * kSlabFloats);
     auto fwd = [&](int l, int k_off, int n_off) {   // w(k,n) = W_l[n_off+n][k_off+k]
         const float* w = W[l]; const int in = widths[l], out = widths[l + 1];
         return [=](int k, int n) { return (k_off + k < in && n_off + n < out) ? w[(size_t)(n_off + n) * in + (k_off + k)] : 0.0f; };
@@ -189,24 +205,24 @@ int pndf_set_weights(pndf_handle* h, const float* flat, size_t n) {
         const float* w = W[l]; const int in = widths[l], out = widths[l + 1];
         return [=](int k, int n) { return (k_off + k < out && n_off + n < in) ? w[(size_t)(k_off + k) * in + (n_off + n)] : 0.0f; };
     };
-    pack_op(s, h->z0_rows, 256, fwd(0, 0, 0));       // F0
-    pack_op(s, 256, 512, fwd(1, 0, 0));              // F1
-    pack_op(s, 512, 512, fwd(2, 0, 0));              // F2a : out features [0,512)
-    pack_op(s, 512, 512, fwd(3, 0, 0));              // F3a : in  features [0,512)
-    pack_op(s, 512, 512, fwd(2, 0, 512));            // F2b : out features [512,1024)
-    pack_op(s, 512, 512, fwd(3, 512, 0));            // F3b : in  features [512,1024)
-    pack_op(s, 512, 256, fwd(4, 0, 0));              // F4
-    pack_op(s, 256, 64, fwd(5, 0, 0));               // F5
-    pack_op(s, 64, 256, bwd(5, 0, 0));               // B5
-    pack_op(s, 256, 512, bwd(4, 0, 0));              // B4
-    pack_op(s, 512, 512, bwd(3, 0, 0));              // B3a : in  features [0,512) of layer 3
-    pack_op(s, 512, 512, bwd(2, 0, 0));              // B2a : out features [0,512) of layer 2
-    pack_op(s, 512, 512, bwd(3, 0, 512));            // B3b
-    pack_op(s, 512, 512, bwd(2, 512, 0));            // B2b
-    pack_op(s, 512, 256, bwd(1, 0, 0));              // B1
-    pack_op(s, 256, 128, bwd(0, 0, 0));              // B0 (in_dim padded to 128)
-    const size_t expect = (size_t)(h->f0_slabs + 2 * slabs_of(256, 512) + 8 * slabs_of(512, 512) + 2 * slabs_of(512, 256) +
-                                   slabs_of(256, 64) + slabs_of(64, 256) + slabs_of(256, 128)) * kSlabFloats;
+    pack_op(s, h->z0_rows, 8, 2, fwd(0, 0, 0));   // F0  (N = 256, split-K)
+    pack_op(s, 256, 8, 1, fwd(1, 0, 0));          // F1
+    pack_op(s, 512, 8, 1, fwd(2, 0, 0));          // F2a : out features [0,512)
+    pack_op(s, 512, 8, 1, fwd(3, 0, 0));          // F3a : in  features [0,512)
+    pack_op(s, 512, 8, 1, fwd(2, 0, 512));        // F2b : out features [512,1024)
+    pack_op(s, 512, 8, 1, fwd(3, 512, 0));        // F3b : in  features [512,1024)
+    pack_op(s, 512, 8, 2, fwd(4, 0, 0));          // F4  (N = 256, split-K)
+    pack_op(s, 256, 1, 1, fwd(5, 0, 0));          // F5  (N = 64)
+    pack_op(s, 64, 8, 2, bwd(5, 0, 0));           // B5  (N = 256, split-K)
+    pack_op(s, 256, 8, 1, bwd(4, 0, 0));          // B4
+    pack_op(s, 512, 8, 1, bwd(3, 0, 0));          // B3a : in  features [0,512) of layer 3
+    pack_op(s, 512, 8, 1, bwd(2, 0, 0));          // B2a : out features [0,512) of layer 2
+    pack_op(s, 512, 8, 1, bwd(3, 0, 512));        // B3b
+    pack_op(s, 512, 8, 1, bwd(2, 512, 0));        // B2b
+    pack_op(s, 512, 8, 2, bwd(1, 0, 0));          // B1  (N = 256, split-K)
+    pack_op(s, 256, 2, 1, bwd(0, 0, 0));          // B0  (N = 128: in_dim padded)
+    const size_t expect = (size_t)(h->f0_slabs + 2 * slabs_of(256, 1, 64) + 8 * slabs_of(512, 1, 64) + 2 * slabs_of(512, 2, 64) +
+                                   slabs_of(256, 1, 8) + slabs_of(64, 2, 64) + slabs_of(256, 1, 16)) * kWarps * kSlabFloats;
     if (s.size() != expect) return fail("internal: slab stream size mismatch");
     // ---- small parameters
     std::vector<float> sm;

@@ -27,10 +27,16 @@ namespace pndf {
 constexpr int kTileM = 32;            // poses per CTA tile
 constexpr int kGemmThreads = 256;     // 8 compute warps; the weight-slab producer role rotates among them
 constexpr int kThreads = 256;         // (256 threads -> 255 registers/thread for the 2x64 fused accumulators)
-constexpr int kSlabFloats = 4096;     // 16 KB weight slab = KC x N floats, KC*N == 4096
+// Weight streaming: every warp owns a PRIVATE 2-stage ring of 4 KB slabs holding only the 64 (16, 8) feature columns
+// that warp multiplies -- R = 1024 / columns rows per slab.  The warp that consumed a slab refills it itself
+// (elected lane, cp.async.bulk), so there is no cross-warp "empty" handshake and no producer rotation at all;
+// warps only meet at the per-op __syncthreads.
+constexpr int kSlabFloats = 1024;     // per-warp slab: R rows x FW feature columns, R*FW == 1024 (4 KB)
 constexpr int kSlabBytes = kSlabFloats * 4;
-constexpr int kStages = 4;
-__host__ __device__ constexpr int slabs_of(int K, int N) { return K * N / kSlabFloats; }
+constexpr int kStages = 2;            // per-warp stages
+constexpr int kWarps = 8;
+// per-warp slab count of an op with K reduction rows split over KG K-groups and FW columns per warp
+__host__ __device__ constexpr int slabs_of(int K, int KG, int FW) { return (K / KG) * FW / kSlabFloats; }
 constexpr int kXS = 85;               // padded row stride of the pose tile
 constexpr int kMaskStride = 2656;     // bytes per pose-group plane of the derivative bit masks
 constexpr int kUnits = 2624;          // hidden units of the DFNet (256+512+1024+512+256+64)
@@ -44,12 +50,12 @@ constexpr int kU1 = 0, kU2 = 256, kU3 = 768, kU4 = 1792, kU5 = 2304, kU6 = 2560;
 constexpr int kSmX = 0;
 constexpr int kSmY = kSmX + 512 * 32 * 4;
 constexpr int kSmRing = kSmY + 512 * 32 * 4;
-constexpr int kSmMask = kSmRing + kStages * kSlabBytes;
+constexpr int kSmMask = kSmRing + kWarps * kStages * kSlabBytes;
 constexpr int kSmXs = kSmMask + 4 * kMaskStride;
 constexpr int kSmNrm = kSmXs + kTileM * kXS * 4;
 constexpr int kSmDv = kSmNrm + 4 * 32 * 4;
 constexpr int kSmBar = kSmDv + 2 * 32 * 4;
-constexpr int kSmTotal = kSmBar + 2 * kStages * 8 + 16;
+constexpr int kSmTotal = kSmBar + kWarps * kStages * 8 + 16;
 
 // debug dump row offsets ([row][32 poses] floats)
 constexpr int kDumpRows = 5504;
@@ -144,32 +150,27 @@ __device__ __forceinline__ float act_eval(float v, int kind, float beta, float& 
     return pos ? v : v * slope;
 }
 
-// Consumer position in the slab ring plus the bookkeeping every thread carries (identically) so that
-// whichever warp is elected for slab g can issue the prefetch of slab g + kStages - 1.
+// Per-warp pipeline state (identical in all lanes of the warp).
 struct Pipe {
     uint32_t stage;       // ring slot of the slab being consumed
     uint32_t phase;       // its mbarrier phase parity
-    uint32_t g;           // slabs consumed so far by this CTA
-    uint32_t pf_left;     // slabs not yet issued
-    uint32_t pf_pos;      // position (in slabs) of the next slab to issue inside the per-step stream
-    uint32_t step_slabs;  // slabs per network pass
-    const char* wsrc;     // slab stream base
+    uint32_t left;        // slabs of this warp not yet issued
+    uint32_t pos;         // position (in per-warp slabs) of the next slab to issue inside the per-step stream
+    uint32_t step_slabs;  // per-warp slabs per network pass
+    const char* wsrc;     // this warp's slab stream base: slab i lives at wsrc + i * kWarps * kSlabBytes
     __device__ __forceinline__ void advance() {
-        ++g;
-        if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-        }
+        stage ^= 1u;
+        phase ^= (stage == 0) ? 1u : 0u;
     }
 };
 
 struct Ctx {
     float* X;
     float* Y;
-    const float* ring;
+    const float* ring;   // THIS WARP's private ring (2 x 4 KB)
+    uint32_t ring_s;
     uint8_t* mask;
-    uint64_t* full;
-    uint64_t* empty;
+    uint32_t full_s;   // shared-space address of this warp's two 'slab landed' mbarriers
     float* dscr;   // this CTA's derivative scratch (softplus) or nullptr
     int tid, lane, mg, ng;
     int ng2, kg;   // split-K ops (N = 256): feature group within a 4-warp K-group, and the K-group (0/1)
@@ -208,19 +209,39 @@ __device__ __forceinline__ void acc_zero(float (&acc)[8][TN]) {
         for (int i = 0; i < 8; ++i) acc[i][j] = 0.0f;
 }
 
-// producer duty for slab g (rotates over the warps): refill the ring slot that slab g-1 occupied with slab
-// g + kStages - 1 of this CTA's stream.  Called by every thread (bookkeeping is replicated), acted on by one lane.
-__device__ __forceinline__ void producer_duty(Pipe& pipe, const Ctx& c) {
-    if (pipe.pf_left != 0) {
-        if ((pipe.g & 7u) == (uint32_t)(c.tid >> 5) && c.lane == 0) {
-            const uint32_t slot = (pipe.stage == 0) ? (kStages - 1) : (pipe.stage - 1);
-            if (pipe.g != 0) mbar_wait(&c.empty[slot], (pipe.stage == 0) ? (pipe.phase ^ 1u) : pipe.phase);
-            mbar_arrive_expect_tx(&c.full[slot], kSlabBytes);
-            bulk_g2s(const_cast<float*>(c.ring) + slot * kSlabFloats, pipe.wsrc + (size_t)pipe.pf_pos * kSlabBytes, kSlabBytes,
-                     &c.full[slot]);
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_s(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+// The warp has finished reading ring slot `stage` (caller did __syncwarp): refill it with the warp's next slab.
+__device__ __forceinline__ void refill(Pipe& pipe, const Ctx& c, uint32_t stage) {
+    if (pipe.left != 0) {
+        if (c.lane == 0) {
+            const uint32_t bar = c.full_s + stage * 8;
+            mbar_expect_tx_s(bar, kSlabBytes);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             c.ring_s + stage * kSlabBytes),
+                         "l"(pipe.wsrc + (size_t)pipe.pos * (kWarps * kSlabBytes)), "r"((uint32_t)kSlabBytes), "r"(bar)
+                         : "memory");
         }
-        --pipe.pf_left;
-        if (++pipe.pf_pos == pipe.step_slabs) pipe.pf_pos = 0;
+        --pipe.left;
+        if (++pipe.pos == pipe.step_slabs) pipe.pos = 0;
     }
 }
 
@@ -230,12 +251,13 @@ struct Operands {
     float b[TN];
 };
 
-// operands of one k-step: 8 pose values of this thread's pose group, TN weights of its feature group
-template <int TN, int KG = 1>
+// operands of one k-step: 8 pose values of this thread's pose group (row k of the activation tile), TN weights of
+// its feature group (row `r` of the warp's slab, FW columns: [32 low features | 32 high features] for TN == 8)
+template <int TN>
 __device__ __forceinline__ void load_operands(Operands<TN>& o, const float* __restrict__ in, int k, const float* __restrict__ w,
-                                              int kk, const Ctx& c) {
-    constexpr int N = 64 * TN / KG;
-    const int ng = ngv<KG>(c);
+                                              int r, const Ctx& c) {
+    constexpr int FW = 8 * TN;
+    const int ngl = c.lane & 7;
     const int key = (k >> 2) & 7;
     const float* row = in + k * 32;
     const float4 a0 = *reinterpret_cast<const float4*>(row + (((c.mg * 2) ^ key) << 2));
@@ -243,18 +265,18 @@ __device__ __forceinline__ void load_operands(Operands<TN>& o, const float* __re
     o.a[0] = a0.x; o.a[1] = a0.y; o.a[2] = a0.z; o.a[3] = a0.w;
     o.a[4] = a1.x; o.a[5] = a1.y; o.a[6] = a1.z; o.a[7] = a1.w;
     if (TN == 8) {
-        const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + ng * 4);
-        const float4 b1 = *reinterpret_cast<const float4*>(w + kk * N + N / 2 + ng * 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(w + r * FW + ngl * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(w + r * FW + 32 + ngl * 4);
         o.b[0] = b0.x; o.b[1 % TN] = b0.y; o.b[2 % TN] = b0.z; o.b[3 % TN] = b0.w;
         o.b[4 % TN] = b1.x; o.b[5 % TN] = b1.y; o.b[6 % TN] = b1.z; o.b[7 % TN] = b1.w;
     } else if (TN == 4) {
-        const float4 b0 = *reinterpret_cast<const float4*>(w + kk * N + ng * 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(w + r * FW + ngl * 4);
         o.b[0] = b0.x; o.b[1 % TN] = b0.y; o.b[2 % TN] = b0.z; o.b[3 % TN] = b0.w;
     } else if (TN == 2) {
-        const float2 b0 = *reinterpret_cast<const float2*>(w + kk * N + ng * 2);
+        const float2 b0 = *reinterpret_cast<const float2*>(w + r * FW + ngl * 2);
         o.b[0] = b0.x; o.b[1 % TN] = b0.y;
     } else {
-        o.b[0] = w[kk * N + ng];
+        o.b[0] = w[r * FW + ngl];
     }
 }
 
@@ -286,36 +308,30 @@ __device__ __forceinline__ void fma_step(float (&acc)[8][TN], const Operands<TN>
     }
 }
 
-// acc[8 poses][TN feats] += in[k][pose] * w[k][feat] over nslabs weight slabs (KC = kSlabFloats/(64*TN) rows each).
-// The slab body is straight-line code (KC k-steps fully unrolled, ptxas software-pipelines the LDS under the
-// FFMA2s); the only scheduling barriers are the mbarrier wait at the top and the arrive at the bottom, so slabs
-// are made as large as shared memory allows (32 KB -> 1 boundary per 4096 packed FMAs per thread).
+// acc[8 poses][TN feats] += in[k][pose] * w[k][feat] over `nslabs` slabs of this warp's private weight stream
+// (R = 1024/(8*TN) reduction rows each; with KG == 2 the warp's K-group covers rows [kg*K/2, (kg+1)*K/2)).
+// The slab body is straight-line code; the next slab's barrier is probed a few rows in, so the ~90-cycle mbarrier
+// round trip hides under the FMAs; the refill of the slab just consumed is issued by the warp itself.
 template <int TN, int KG = 1>
 __device__ __forceinline__ void gemm_op(float (&acc)[8][TN], const float* __restrict__ in, int nslabs, Pipe& pipe,
                                         const Ctx& c) {
-    constexpr int N = 64 * TN / KG;
-    constexpr int KC = kSlabFloats / N;      // rows per slab
-    constexpr int KR = KC / KG;              // rows of each slab this thread's K-group consumes
-    const int k0 = (KG == 1) ? 0 : c.kg * KR;
-    producer_duty(pipe, c);
-    bool ready = mbar_try_wait(&c.full[pipe.stage], pipe.phase);
+    constexpr int R = kSlabFloats / (8 * TN);
+    const int kbase = (KG == 1) ? 0 : c.kg * (nslabs * R);
+    bool ready = mbar_try_wait_s(c.full_s + pipe.stage * 8, pipe.phase);
     for (int s = 0; s < nslabs; ++s) {
-        if (!ready) mbar_wait(&c.full[pipe.stage], pipe.phase);
+        if (!ready) mbar_wait_s(c.full_s + pipe.stage * 8, pipe.phase);
         const float* __restrict__ w = c.ring + pipe.stage * kSlabFloats;
-        const uint32_t nstage = (pipe.stage + 1 == kStages) ? 0u : pipe.stage + 1;
-        const uint32_t nphase = (pipe.stage + 1 == kStages) ? (pipe.phase ^ 1u) : pipe.phase;
-#pragma unroll (KR > 32 ? 32 : KR)
-        for (int kk = 0; kk < KR; ++kk) {
-            // probe the NEXT slab's barrier early: the ~90-cycle mbarrier round trip hides under this slab's FMAs
-            if (kk == (KR > 8 ? 4 : KR / 2)) ready = mbar_try_wait(&c.full[nstage], nphase);
+        const uint32_t cur = pipe.stage;
+        pipe.advance();
+#pragma unroll (R > 32 ? 32 : R)
+        for (int r = 0; r < R; ++r) {
+            if (r == 4) ready = mbar_try_wait_s(c.full_s + pipe.stage * 8, pipe.phase);
             Operands<TN> o;
-            load_operands<TN, KG>(o, in, s * KC + k0 + kk, w, k0 + kk, c);
+            load_operands<TN>(o, in, kbase + s * R + r, w, r, c);
             fma_step<TN>(acc, o);
         }
         __syncwarp();
-        if (c.lane == 0) mbar_arrive(&c.empty[pipe.stage]);
-        pipe.advance();
-        if (s + 1 < nslabs) producer_duty(pipe, c);
+        refill(pipe, c, cur);
     }
 }
 
@@ -641,32 +657,30 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     float* xs = reinterpret_cast<float*>(smem + kSmXs);
     float* nrm = reinterpret_cast<float*>(smem + kSmNrm);
     float* dval = reinterpret_cast<float*>(smem + kSmDv);   // [32] distance, [32] upstream*out_act'
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmBar);
-    uint64_t* empty = full + kStages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmBar);   // [warp][stage]: "slab landed"
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kGemmThreads / 32);
-        }
+        for (int i = 0; i < kWarps * kStages; ++i) mbar_init(&full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     // forward ops: F0(f0_slabs) F1(32) [F2a(64) F3a(64) F2b(64) F3b(64)] F4(32) F5(4)
     // reverse ops: B5(4) B4(32) [B3a(64) B2a(64) B3b(64) B2b(64)] B1(32) B0(8)
-    constexpr int kS1 = slabs_of(256, 512), kS23 = slabs_of(512, 512), kS4 = slabs_of(512, 256), kS5 = slabs_of(256, 64);
-    constexpr int kSB5 = slabs_of(64, 256), kSB0 = slabs_of(256, 128);
+    // per-warp slab counts of the ops (4 KB each): forward F0 F1 [F2a F3a F2b F3b] F4 F5, reverse B5 B4 [B3a B2a B3b B2b] B1 B0
+    constexpr int kS1 = slabs_of(256, 1, 64), kS23 = slabs_of(512, 1, 64), kS4 = slabs_of(512, 2, 64), kS5 = slabs_of(256, 1, 8);
+    constexpr int kSB5 = slabs_of(64, 2, 64), kSB0 = slabs_of(256, 1, 16);
     const int fwd_slabs = p.f0_slabs + kS1 + 4 * kS23 + kS4 + kS5;
     constexpr int bwd_slabs = kSB5 + kS1 + 4 * kS23 + kS4 + kSB0;
     const int step_slabs = fwd_slabs + (kGrad ? bwd_slabs : 0);
 
     // ------------------------------------------------------------------ compute warps
     Ctx c;
-    c.X = X; c.Y = Y; c.ring = ring; c.mask = mask; c.full = full; c.empty = empty;
+    c.X = X; c.Y = Y; c.ring = ring + warp * (kStages * kSlabFloats); c.mask = mask;
+    c.ring_s = smem_u32(c.ring); c.full_s = smem_u32(full + warp * kStages);
     c.tid = tid; c.lane = lane; c.mg = lane >> 3; c.ng = warp * 8 + (lane & 7);
     c.ng2 = (warp & 3) * 8 + (lane & 7); c.kg = warp >> 2;
     c.df_act = p.df_act; c.df_beta = p.df_beta;
@@ -675,22 +689,16 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     EncLane enc;
     enc.l = lane & 7; enc.base = lane & 24; enc.m = warp * 4 + (lane >> 3);
     Pipe pipe;
-    pipe.stage = 0; pipe.phase = 0; pipe.g = 0;
+    pipe.stage = 0; pipe.phase = 0;
     pipe.step_slabs = (uint32_t)step_slabs;
-    pipe.wsrc = reinterpret_cast<const char*>(p.wstream);
+    pipe.wsrc = reinterpret_cast<const char*>(p.wstream) + (size_t)warp * kSlabBytes;
     {
         const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        const uint32_t total = (uint32_t)my_tiles * (uint32_t)p.steps * (uint32_t)step_slabs;
-        // prologue: the first kStages-1 slabs
-        const uint32_t pro = min(total, (uint32_t)(kStages - 1));
-        if (tid == 0) {
-            for (uint32_t s = 0; s < pro; ++s) {
-                mbar_arrive_expect_tx(&full[s], kSlabBytes);
-                bulk_g2s(ring + s * kSlabFloats, pipe.wsrc + (size_t)s * kSlabBytes, kSlabBytes, &full[s]);
-            }
-        }
-        pipe.pf_left = total - pro;
-        pipe.pf_pos = pro % (uint32_t)step_slabs;
+        pipe.left = (uint32_t)my_tiles * (uint32_t)p.steps * (uint32_t)step_slabs;
+        pipe.pos = 0;
+        // prologue: fill both stages of this warp's ring
+        refill(pipe, c, 0);
+        refill(pipe, c, 1);
     }
 
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
