@@ -40,6 +40,7 @@ struct pndf_handle {
     size_t off_bias[7];
     size_t off_w6 = 0, off_enc = 0;
     float* d_scratch = nullptr;   // softplus derivative scratch, num_sms * kUnits * 32 floats
+    float* d_z0 = nullptr;        // encoder feature stash, num_sms * 128 * 32 floats
     int f0_slabs = 0, z0_rows = 0;
     int64_t launches = 0;
     // host pipeline (pndf_project_host)
@@ -110,6 +111,7 @@ int launch(pndf_handle* h, KParams& p, bool grad, cudaStream_t st) {
     p.w6 = h->d_small + h->off_w6;
     p.encw = h->cfg.use_enc ? h->d_small + h->off_enc : nullptr;
     p.dscratch = h->d_scratch;
+    p.z0scratch = h->d_z0;
     p.ntiles = (int)((p.B + kTileM - 1) / kTileM);
     p.use_enc = h->cfg.use_enc; p.enc_act = h->cfg.enc_act; p.df_act = h->cfg.df_act;
     p.enc_beta = h->cfg.enc_beta; p.df_beta = h->cfg.df_beta;
@@ -154,6 +156,7 @@ int pndf_create(const pndf_config* cfg, pndf_handle** out) {
     h->f0_slabs = slabs_of(h->z0_rows, 2, 64);
     CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
     CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
+    CUDA_OK(cudaMalloc(&h->d_z0, (size_t)h->num_sms * 128 * 32 * sizeof(float)));
     if (cfg->df_act == PNDF_ACT_SOFTPLUS)
         CUDA_OK(cudaMalloc(&h->d_scratch, (size_t)h->num_sms * kUnits * 32 * sizeof(float)));
     *out = h;
@@ -166,6 +169,7 @@ int pndf_destroy(pndf_handle* h) {
     cudaFree(h->d_wstream);
     cudaFree(h->d_small);
     cudaFree(h->d_scratch);
+    cudaFree(h->d_z0);
     for (int i = 0; i < 4; ++i) cudaFree(h->d_dn[i]);
     for (int i = 0; i < 2; ++i) {
         if (h->hs[i]) cudaStreamDestroy(h->hs[i]);

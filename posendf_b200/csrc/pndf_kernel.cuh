@@ -52,7 +52,8 @@ constexpr int kSmY = kSmX + 512 * 32 * 4;
 constexpr int kSmRing = kSmY + 512 * 32 * 4;
 constexpr int kSmMask = kSmRing + kWarps * kStages * kSlabBytes;
 constexpr int kSmXs = kSmMask + 4 * kMaskStride;
-constexpr int kSmNrm = kSmXs + kTileM * kXS * 4;
+constexpr int kSmQs = kSmXs + kTileM * kXS * 4;      // column-normalised poses q = x / n (what the encoder eats)
+constexpr int kSmNrm = kSmQs + kTileM * kXS * 4;
 constexpr int kSmDv = kSmNrm + 4 * 32 * 4;
 constexpr int kSmBar = kSmDv + 2 * 32 * 4;
 constexpr int kSmTotal = kSmBar + kWarps * kStages * 8 + 16;
@@ -74,6 +75,7 @@ struct KParams {
     float* grad;              // B x 84 (or B x 63 in prior mode) or nullptr
     const float* g_up;        // B or nullptr
     float* dscratch;          // per-CTA fp32 derivative scratch (softplus) or nullptr
+    float* z0scratch;         // per-CTA stash of the encoder features (128 x 32 floats), L2 resident
     float* dbg;               // debug dump or nullptr
     long long B;
     int ntiles;
@@ -151,6 +153,15 @@ __device__ __forceinline__ float act_eval(float v, int kind, float beta, float& 
 }
 
 // Per-warp pipeline state (identical in all lanes of the warp).
+// compile-time variant for the encoder: SOFT = softplus(beta = par), else piecewise-linear with slope = par
+template <bool SOFT>
+__device__ __forceinline__ float act_t(float v, float par, float& deriv) {
+    if (SOFT) return act_eval(v, ACT_SOFTPLUS, par, deriv);
+    const bool pos = v > 0.0f;
+    deriv = pos ? 1.0f : par;
+    return pos ? v : v * par;
+}
+
 struct Pipe {
     uint32_t stage;       // ring slot of the slab being consumed
     uint32_t phase;       // its mbarrier phase parity
@@ -515,15 +526,14 @@ __device__ __forceinline__ float grp_get(float v, int src_l, const EncLane& e) {
 
 // first part shared by forward and reverse: u, the two hidden units of this lane, all 10 hidden values, and this
 // lane's output feature (o = min(l,5)).  d1a/d1b/d2 = activation derivatives at this lane's units.
-__device__ __forceinline__ void bone_forward(const float* __restrict__ w, bool root, const float* xs, const float* nrm,
-                                             const float* feat, int i, int par, const EncLane& e, const KParams& p,
-                                             float (&u)[10], float (&h)[10], float& f, float& d1a, float& d1b, float& d2) {
+// qs = column-normalised pose tile [pose][85]; apar = slope (relu 0 / lrelu 0.01) or softplus beta.
+template <bool SOFT>
+__device__ __forceinline__ void bone_forward(const float* __restrict__ w, bool root, const float* qs, const float* feat, int i,
+                                             int par, const EncLane& e, float apar, float (&u)[10], float (&h)[10], float& f,
+                                             float& d1a, float& d1b, float& d2) {
     const int fin = root ? 4 : 10;
 #pragma unroll
-    for (int cpt = 0; cpt < 4; ++cpt) {
-        const float x = xs[e.m * kXS + i * 4 + cpt];
-        u[cpt] = p.normalise ? x / nrm[cpt * 32 + e.m] : x;
-    }
+    for (int cpt = 0; cpt < 4; ++cpt) u[cpt] = qs[e.m * kXS + i * 4 + cpt];
 #pragma unroll
     for (int r = 0; r < 6; ++r) u[4 + r] = root ? 0.0f : feat[swz(par * 6 + r, e.m)];
     const int oa = e.l, ob = min(8 + e.l, 9);
@@ -545,8 +555,8 @@ __device__ __forceinline__ void bone_forward(const float* __restrict__ w, bool r
             sb = fmaf(w1[ob * 10 + k], u[k], sb);
         }
     }
-    const float ha = act_eval(sa, p.enc_act, p.enc_beta, d1a);
-    const float hb = act_eval(sb, p.enc_act, p.enc_beta, d1b);
+    const float ha = act_t<SOFT>(sa, apar, d1a);
+    const float hb = act_t<SOFT>(sb, apar, d1b);
 #pragma unroll
     for (int k = 0; k < 8; ++k) h[k] = grp_get(ha, k, e);
     h[8] = grp_get(hb, 0, e);
@@ -555,32 +565,38 @@ __device__ __forceinline__ void bone_forward(const float* __restrict__ w, bool r
     float s2 = b2[o];
 #pragma unroll
     for (int k = 0; k < 10; ++k) s2 = fmaf(w2[o * 10 + k], h[k], s2);
-    f = act_eval(s2, p.enc_act, p.enc_beta, d2);
+    f = act_t<SOFT>(s2, apar, d2);
 }
 
-// forward encoder for this lane's pose; features are written as rows [i*6+o][m] of `feat`.
-__device__ __forceinline__ void encoder_forward(const float* encw, const float* xs, const float* nrm, float* feat,
-                                                const EncLane& e, const KParams& p) {
+// forward encoder for this lane's pose; features are written as rows [i*6+o][m] of `feat` (and, if stash != nullptr,
+// to the CTA's L2-resident stash so that the reverse pass does not have to recompute them).
+template <bool SOFT>
+__device__ __forceinline__ void encoder_forward(const float* encw, const float* qs, float* feat, float* stash, const EncLane& e,
+                                                float apar) {
     for (int i = 0; i < 21; ++i) {
         const int par = c_parent[i];
         float u[10], h[10], f, d1a, d1b, d2;
-        bone_forward(encw + enc_off(i), par < 0, xs, nrm, feat, i, par, e, p, u, h, f, d1a, d1b, d2);
-        if (e.l < 6) feat[swz(i * 6 + e.l, e.m)] = f;
+        bone_forward<SOFT>(encw + enc_off(i), par < 0, qs, feat, i, par, e, apar, u, h, f, d1a, d1b, d2);
+        if (e.l < 6) {
+            feat[swz(i * 6 + e.l, e.m)] = f;
+            if (stash != nullptr) stash[(i * 6 + e.l) * 32 + e.m] = f;
+        }
         __syncwarp();
     }
 }
 
-// reverse encoder: features in `feat` (recomputed), feature gradients in rows [0,126) of `gbuf` (accumulated in
-// place, reverse joint order is a reverse topological order), quaternion gradients -> rows [128+e] of `gbuf`.
-__device__ __forceinline__ void encoder_backward(const float* encw, const float* xs, const float* nrm, const float* feat,
-                                                 float* gbuf, const EncLane& e, const KParams& p) {
+// reverse encoder: features in `feat`, feature gradients in rows [0,126) of `gbuf` (accumulated in place, reverse
+// joint order is a reverse topological order), quaternion gradients -> rows [128+e] of `gbuf`.
+template <bool SOFT>
+__device__ __forceinline__ void encoder_backward(const float* encw, const float* qs, const float* feat, float* gbuf,
+                                                 const EncLane& e, float apar) {
     for (int i = 20; i >= 0; --i) {
         const int par = c_parent[i];
         const bool root = par < 0;
         const int fin = root ? 4 : 10;
         const float* w = encw + enc_off(i);
         float u[10], h[10], f, d1a, d1b, d2;
-        bone_forward(w, root, xs, nrm, feat, i, par, e, p, u, h, f, d1a, d1b, d2);
+        bone_forward<SOFT>(w, root, qs, feat, i, par, e, apar, u, h, f, d1a, d1b, d2);
         const float* w1 = w;
         const float* w2 = w + 10 * fin + 10;
         // t[o] = fbar[o] * act'(pre2[o]) on lane o (< 6)
@@ -655,6 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     // encoder weights (14 KB) are staged into the idle upper half of X around the encoder phases only
     float* encw = X + kEncStageRow * 32;
     float* xs = reinterpret_cast<float*>(smem + kSmXs);
+    float* qs = reinterpret_cast<float*>(smem + kSmQs);
     float* nrm = reinterpret_cast<float*>(smem + kSmNrm);
     float* dval = reinterpret_cast<float*>(smem + kSmDv);   // [32] distance, [32] upstream*out_act'
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmBar);   // [warp][stage]: "slab landed"
@@ -733,7 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
 
         for (int st = 0; st < p.steps; ++st) {
             float* dbg_s = (st == 0) ? dbg : nullptr;
-            // ---- column norms + encoder: 8 lanes per pose, 4 poses per warp
+            // ---- column norms, q = x / n, encoder: 8 lanes per pose, 4 poses per warp
             {
                 const int cpt = enc.l & 3, hf = enc.l >> 2;
                 if (p.normalise) {
@@ -743,21 +760,20 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                         sq = fmaf(x, x, sq);
                     }
                     sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-                    if (hf == 0) nrm[cpt * 32 + enc.m] = fmaxf(sqrtf(sq), 1e-12f);
-                    __syncwarp();
+                    const float n = fmaxf(sqrtf(sq), 1e-12f);
+                    if (hf == 0) nrm[cpt * 32 + enc.m] = n;
+                    for (int j = hf; j < 21; j += 2) qs[enc.m * kXS + j * 4 + cpt] = xs[enc.m * kXS + j * 4 + cpt] / n;
+                } else {
+                    for (int j = hf; j < 21; j += 2) qs[enc.m * kXS + j * 4 + cpt] = xs[enc.m * kXS + j * 4 + cpt];
                 }
+                __syncwarp();
                 if (p.use_enc) {
-                    encoder_forward(encw, xs, nrm, X, enc, p);
+                    float* stash = (kGrad && p.z0scratch != nullptr) ? p.z0scratch + (size_t)blockIdx.x * 128 * 32 : nullptr;
+                    if (p.enc_act == ACT_SOFTPLUS) encoder_forward<true>(encw, qs, X, stash, enc, p.enc_beta);
+                    else encoder_forward<false>(encw, qs, X, stash, enc, (p.enc_act == ACT_RELU) ? 0.0f : 0.01f);
                     if (enc.l < 2) X[swz(126 + enc.l, enc.m)] = 0.0f;
                 } else {
-                    for (int e = enc.l; e < 96; e += 8) {
-                        float v = 0.0f;
-                        if (e < 84) {
-                            const float x = xs[enc.m * kXS + e];
-                            v = p.normalise ? x / nrm[(e & 3) * 32 + enc.m] : x;
-                        }
-                        X[swz(e, enc.m)] = v;
-                    }
+                    for (int e = enc.l; e < 96; e += 8) X[swz(e, enc.m)] = (e < 84) ? qs[enc.m * kXS + e] : 0.0f;
                 }
             }
             gemm_bar();
@@ -909,15 +925,17 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             dump_rows(dbg_s, 5376, Y, 128, tid);
 
             // ---- encoder reverse + normalise Jacobian + step: 8 lanes per pose
-            if (p.use_enc) {   // X is free again: park the encoder weights in its upper half
+            if (p.use_enc) {   // X is free again: park the encoder weights in its upper half, bring the features back
                 for (int i = tid; i < kEncFloats; i += kGemmThreads) encw[i] = __ldg(p.encw + i);
+                const float* stash = p.z0scratch + (size_t)blockIdx.x * 128 * 32;
+                for (int idx = tid; idx < 126 * 32; idx += kGemmThreads) X[swz(idx >> 5, idx & 31)] = stash[idx];
                 gemm_bar();
             }
             {
                 const int m = enc.m;
                 if (p.use_enc) {
-                    encoder_forward(encw, xs, nrm, X, enc, p);          // recompute features (X is free)
-                    encoder_backward(encw, xs, nrm, X, Y, enc, p);      // qbar -> Y rows [128, 212)
+                    if (p.enc_act == ACT_SOFTPLUS) encoder_backward<true>(encw, qs, X, Y, enc, p.enc_beta);
+                    else encoder_backward<false>(encw, qs, X, Y, enc, (p.enc_act == ACT_RELU) ? 0.0f : 0.01f);   // qbar -> Y rows [128, 212)
                 } else {
                     for (int e = enc.l; e < 84; e += 8) Y[swz(128 + e, m)] = Y[swz(e, m)];
                     __syncwarp();
@@ -928,7 +946,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 float n = 1.0f, dot = 0.0f;
                 if (p.normalise) {
                     n = nrm[cpt * 32 + m];
-                    for (int j = hf; j < 21; j += 2) dot = fmaf(xs[m * kXS + j * 4 + cpt] / n, Y[swz(128 + j * 4 + cpt, m)], dot);
+                    for (int j = hf; j < 21; j += 2) dot = fmaf(qs[m * kXS + j * 4 + cpt], Y[swz(128 + j * 4 + cpt, m)], dot);
                     dot += __shfl_xor_sync(0xffffffffu, dot, 4);
                     if (n <= 1e-12f) dot = 0.0f;   // clamp active: map is x/eps, Jacobian is I/eps
                 }
@@ -936,7 +954,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                     const int e = j * 4 + cpt;
                     const float x = xs[m * kXS + e];
                     float g = Y[swz(128 + e, m)];
-                    if (p.normalise) g = (g - (x / n) * dot) / n;
+                    if (p.normalise) g = (g - qs[m * kXS + e] * dot) / n;
                     Y[swz(128 + e, m)] = g;
                     if (p.do_step) xs[m * kXS + e] = __fsub_rn(x, __fmul_rn(d, g));   // two roundings, as torch's x - d*g
                 }
