@@ -334,12 +334,37 @@ __device__ __forceinline__ void gemm_op(float (&acc)[8][TN], const float* __rest
         const float* __restrict__ w = c.ring + pipe.stage * kSlabFloats;
         const uint32_t cur = pipe.stage;
         pipe.advance();
+        if (TN == 8) {
+            // 16 rows starting at a multiple of 16: the swizzle key (row>>2)&7 is kb, kb+1, kb+2, kb+3 with kb in {0,4},
+            // so the thread's two 16-byte pose chunks sit at ((2mg ^ kb) ^ j) and that ^ 1 for row quad j: four offsets per
+            // slab, every row is then base + immediate -- no address arithmetic between the FFMA2s.
+            const int k0 = kbase + s * R;
+            const float* __restrict__ rows = in + k0 * 32;
+            const int cb = (c.mg * 2) ^ ((k0 >> 2) & 4);
+            const int ngl4 = (c.lane & 7) * 4;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (r == 4) ready = mbar_try_wait_s(c.full_s + pipe.stage * 8, pipe.phase);
+                const int ca = (cb ^ (r >> 2)) << 2;
+                const float4 a0 = *reinterpret_cast<const float4*>(rows + r * 32 + ca);
+                const float4 a1 = *reinterpret_cast<const float4*>(rows + r * 32 + (ca ^ 4));
+                const float4 b0 = *reinterpret_cast<const float4*>(w + r * 64 + ngl4);
+                const float4 b1 = *reinterpret_cast<const float4*>(w + r * 64 + 32 + ngl4);
+                Operands<TN> o;
+                o.a[0] = a0.x; o.a[1] = a0.y; o.a[2] = a0.z; o.a[3] = a0.w;
+                o.a[4] = a1.x; o.a[5] = a1.y; o.a[6] = a1.z; o.a[7] = a1.w;
+                o.b[0] = b0.x; o.b[1 % TN] = b0.y; o.b[2 % TN] = b0.z; o.b[3 % TN] = b0.w;
+                o.b[4 % TN] = b1.x; o.b[5 % TN] = b1.y; o.b[6 % TN] = b1.z; o.b[7 % TN] = b1.w;
+                fma_step<TN>(acc, o);
+            }
+        } else {
 #pragma unroll (R > 32 ? 32 : R)
-        for (int r = 0; r < R; ++r) {
-            if (r == 4) ready = mbar_try_wait_s(c.full_s + pipe.stage * 8, pipe.phase);
-            Operands<TN> o;
-            load_operands<TN>(o, in, kbase + s * R + r, w, r, c);
-            fma_step<TN>(acc, o);
+            for (int r = 0; r < R; ++r) {
+                if (r == 4) ready = mbar_try_wait_s(c.full_s + pipe.stage * 8, pipe.phase);
+                Operands<TN> o;
+                load_operands<TN>(o, in, kbase + s * R + r, w, r, c);
+                fma_step<TN>(acc, o);
+            }
         }
         __syncwarp();
         refill(pipe, c, cur);
