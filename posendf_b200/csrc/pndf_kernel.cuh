@@ -135,17 +135,20 @@ __device__ __forceinline__ void gemm_bar() { __syncthreads(); }
 // (row>>2)&7 so that the 8 lanes of a warp that own different feature groups hit different banks.
 __device__ __forceinline__ int swz(int row, int m) { return row * 32 + (((((m >> 2) ^ (row >> 2)) & 7) << 2) | (m & 3)); }
 
+// nn.Softplus(beta) with torch's threshold 20, branch-free (the GEMM epilogues evaluate it 84 000 times per tile):
+// value log1p(exp(beta x))/beta and derivative exp/(1+exp) = torch's softplus_backward z/(z+1); above the threshold
+// both are selected to x and 1.  exp is clamped so the unused lane of the select never overflows.
+__device__ __forceinline__ float softplus_eval(float v, float beta, float inv_beta, float& deriv) {
+    const float bx = v * beta;
+    const bool lin = bx > 20.0f;
+    const float e = expf(fminf(bx, 20.0f));
+    const float r = __frcp_rn(e + 1.0f);
+    deriv = lin ? 1.0f : e * r;
+    return lin ? v : log1pf(e) * inv_beta;
+}
+
 __device__ __forceinline__ float act_eval(float v, int kind, float beta, float& deriv) {
-    if (kind == ACT_SOFTPLUS) {
-        float bx = v * beta;
-        if (bx > 20.0f) {
-            deriv = 1.0f;
-            return v;
-        }
-        float e = expf(bx);
-        deriv = e / (e + 1.0f);
-        return log1pf(e) / beta;
-    }
+    if (kind == ACT_SOFTPLUS) return softplus_eval(v, beta, 1.0f / beta, deriv);
     float slope = (kind == ACT_RELU) ? 0.0f : 0.01f;
     bool pos = v > 0.0f;
     deriv = pos ? 1.0f : slope;
@@ -186,7 +189,7 @@ struct Ctx {
     int tid, lane, mg, ng;
     int ng2, kg;   // split-K ops (N = 256): feature group within a 4-warp K-group, and the K-group (0/1)
     int df_act;
-    float df_beta;
+    float df_beta, df_inv_beta;
 };
 
 // KG = number of K-groups an op is split into: KG == 1, all 8 warps tile N = 64*TN features; KG == 2 (split-K, used for
@@ -424,7 +427,7 @@ __device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* o
             const int f = feat_of<TN, KG>(ng, j);
             float z[8], dv[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) z[i] = act_eval(acc[i][j], ACT_SOFTPLUS, c.df_beta, dv[i]);
+            for (int i = 0; i < 8; ++i) z[i] = softplus_eval(acc[i][j], c.df_beta, c.df_inv_beta, dv[i]);
             store_row8(out, f, c.mg, z);
             if (keep_deriv) {
                 float* p = c.dscr + (size_t)(unit_base + f) * 32 + c.mg * 8;
@@ -725,7 +728,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     c.ring_s = smem_u32(c.ring); c.full_s = smem_u32(full + warp * kStages);
     c.tid = tid; c.lane = lane; c.mg = lane >> 3; c.ng = warp * 8 + (lane & 7);
     c.ng2 = (warp & 3) * 8 + (lane & 7); c.kg = warp >> 2;
-    c.df_act = p.df_act; c.df_beta = p.df_beta;
+    c.df_act = p.df_act; c.df_beta = p.df_beta; c.df_inv_beta = 1.0f / p.df_beta;
     c.dscr = p.dscratch ? p.dscratch + (size_t)blockIdx.x * kUnits * 32 : nullptr;
     const bool keep = kGrad;
     EncLane enc;
