@@ -34,6 +34,8 @@ SYMBOLS = {
     "pndf_denoise_prior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pndf_debug_dump_floats": (C.c_int, [C.POINTER(C.c_size_t)]),
     "pndf_forward_grad_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pndf_forward_grad_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pndf_forward_tangent_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pndf_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pndf_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "pndf_num_sms": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),

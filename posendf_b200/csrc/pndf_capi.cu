@@ -103,7 +103,7 @@ void pack_op(std::vector<float>& out, int K, int TN, int KG, F get) {
         }
 }
 
-int launch(pndf_handle* h, KParams& p, bool grad, cudaStream_t st) {
+int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st) {
     if (!h->have_weights) return fail("pndf_set_weights has not been called");
     if (p.B <= 0) return 0;
     p.wstream = h->d_wstream;
@@ -117,10 +117,12 @@ int launch(pndf_handle* h, KParams& p, bool grad, cudaStream_t st) {
     p.enc_beta = h->cfg.enc_beta; p.df_beta = h->cfg.df_beta;
     p.f0_slabs = h->f0_slabs; p.z0_rows = h->z0_rows; p.in_dim = h->cfg.in_dim;
     const int grid = std::min(p.ntiles, h->num_sms);
-    if (grad)
-        pndf_fused_kernel<true><<<grid, kThreads, kSmTotal, st>>>(p);
+    if (mode == 1)
+        pndf_fused_kernel<1><<<grid, kThreads, kSmTotal, st>>>(p);
+    else if (mode == 2)
+        pndf_fused_kernel<2><<<grid, kThreads, kSmTotal, st>>>(p);
     else
-        pndf_fused_kernel<false><<<grid, kThreads, kSmTotal, st>>>(p);
+        pndf_fused_kernel<0><<<grid, kThreads, kSmTotal, st>>>(p);
     CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -154,8 +156,9 @@ int pndf_create(const pndf_config* cfg, pndf_handle** out) {
     h->num_sms = prop.multiProcessorCount;
     h->z0_rows = cfg->use_enc ? 128 : 96;
     h->f0_slabs = slabs_of(h->z0_rows, 2, 64);
-    CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
-    CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
+    CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
+    CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
+    CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
     CUDA_OK(cudaMalloc(&h->d_z0, (size_t)h->num_sms * 128 * 32 * sizeof(float)));
     if (cfg->df_act == PNDF_ACT_SOFTPLUS)
         CUDA_OK(cudaMalloc(&h->d_scratch, (size_t)h->num_sms * kUnits * 32 * sizeof(float)));
@@ -256,7 +259,7 @@ int pndf_forward(pndf_handle* h, const float* pose_dev, int64_t B, int normalise
     CUDA_OK(cudaSetDevice(h->cfg.device));
     KParams p{};
     p.pose_in = pose_dev; p.dist = dist_dev; p.B = B; p.steps = 1; p.normalise = normalise; p.input_kind = IN_QUAT;
-    return launch(h, p, false, (cudaStream_t)stream);
+    return launch(h, p, 0, (cudaStream_t)stream);
 }
 
 int pndf_forward_grad(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, const float* g_up_dev,
@@ -268,7 +271,7 @@ int pndf_forward_grad(pndf_handle* h, const float* pose_dev, int64_t B, int norm
     KParams p{};
     p.pose_in = pose_dev; p.dist = dist_dev; p.grad = grad_dev; p.g_up = g_up_dev; p.B = B; p.steps = 1;
     p.normalise = normalise; p.input_kind = IN_QUAT;
-    return launch(h, p, true, (cudaStream_t)stream);
+    return launch(h, p, 1, (cudaStream_t)stream);
 }
 
 int pndf_project(pndf_handle* h, float* pose_dev, int64_t B, int steps, int renorm, float* dist_dev, void* stream) {
@@ -280,7 +283,7 @@ int pndf_project(pndf_handle* h, float* pose_dev, int64_t B, int steps, int reno
     KParams p{};
     p.pose_in = pose_dev; p.pose_out = pose_dev; p.dist = dist_dev; p.B = B; p.steps = steps; p.do_step = 1;
     p.renorm = renorm; p.normalise = 1; p.input_kind = IN_QUAT;
-    return launch(h, p, true, (cudaStream_t)stream);
+    return launch(h, p, 1, (cudaStream_t)stream);
 }
 
 int pndf_prior_grad(pndf_handle* h, const float* aa_dev, int64_t B, const float* g_up_dev, float* dist_dev,
@@ -292,7 +295,7 @@ int pndf_prior_grad(pndf_handle* h, const float* aa_dev, int64_t B, const float*
     KParams p{};
     p.pose_in = aa_dev; p.dist = dist_dev; p.grad = grad_aa_dev; p.g_up = g_up_dev; p.B = B; p.steps = 1;
     p.normalise = 1; p.input_kind = IN_AXIS_ANGLE;
-    return launch(h, p, true, (cudaStream_t)stream);
+    return launch(h, p, 1, (cudaStream_t)stream);
 }
 
 int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out_host, float* dist_host, int64_t B,
@@ -319,7 +322,7 @@ int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out
         KParams p{};
         p.pose_in = h->d_chunk[which]; p.pose_out = h->d_chunk[which]; p.dist = h->d_chunk_dist[which]; p.B = nb;
         p.steps = steps; p.do_step = 1; p.renorm = renorm; p.normalise = 1; p.input_kind = IN_QUAT;
-        if (launch(h, p, true, st)) return 1;
+        if (launch(h, p, 1, st)) return 1;
         CUDA_OK(cudaMemcpyAsync(pose_out_host + off * 84, h->d_chunk[which], nb * 84 * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (dist_host) CUDA_OK(cudaMemcpyAsync(dist_host + off, h->d_chunk_dist[which], nb * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
@@ -360,7 +363,7 @@ int pndf_denoise_prior(pndf_handle* h, float* aa_dev, int64_t S, int64_t T, int 
         for (int i = 0; i < steps_per_iter; ++i, ++t) {
             KParams p{};
             p.pose_in = aa_dev; p.dist = dist; p.grad = graw; p.B = B; p.steps = 1; p.normalise = 1; p.input_kind = IN_AXIS_ANGLE;
-            if (launch(h, p, true, st)) return 1;
+            if (launch(h, p, 1, st)) return 1;
             p1 *= b1; p2 *= b2;
             AdamParams ap;
             ap.lr = lr; ap.beta1 = (float)b1; ap.beta2 = (float)b2; ap.eps = 1e-8f;
@@ -387,7 +390,31 @@ int pndf_forward_grad_debug(pndf_handle* h, const float* pose_dev, int64_t B, in
     KParams p{};
     p.pose_in = pose_dev; p.dist = dist_dev; p.grad = grad_dev; p.B = std::min<int64_t>(B, 32); p.steps = 1;
     p.normalise = normalise; p.input_kind = IN_QUAT; p.dbg = dump_dev;
-    return launch(h, p, true, (cudaStream_t)stream);
+    return launch(h, p, 1, (cudaStream_t)stream);
+}
+
+int pndf_forward_grad_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, float* dist_dev, float* grad_dev,
+                             float* dump_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (B == 0) return 0;
+    if (B < 0 || !pose_dev || !grad_dev || !dump_dev) return fail("null argument");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    KParams p{};
+    p.pose_in = pose_dev; p.dist = dist_dev; p.grad = grad_dev; p.B = B; p.steps = 1;
+    p.normalise = normalise; p.input_kind = IN_QUAT; p.dbg = dump_dev; p.dump_all = 1;
+    return launch(h, p, 1, (cudaStream_t)stream);
+}
+
+int pndf_forward_tangent_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, const float* tan_dev,
+                                float* dump_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (B == 0) return 0;
+    if (B < 0 || !pose_dev || !tan_dev || !dump_dev) return fail("null argument");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    KParams p{};
+    p.pose_in = pose_dev; p.B = B; p.steps = 1; p.normalise = normalise; p.input_kind = IN_QUAT;
+    p.dbg = dump_dev; p.dump_all = 1; p.tan_in = tan_dev;
+    return launch(h, p, 2, (cudaStream_t)stream);
 }
 
 int pndf_launch_count(pndf_handle* h, int64_t* n) {

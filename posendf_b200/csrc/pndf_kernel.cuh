@@ -76,7 +76,9 @@ struct KParams {
     const float* g_up;        // B or nullptr
     float* dscratch;          // per-CTA fp32 derivative scratch (softplus) or nullptr
     float* z0scratch;         // per-CTA stash of the encoder features (128 x 32 floats), L2 resident
-    float* dbg;               // debug dump or nullptr
+    float* dbg;               // dump of every intermediate tile ([row][32 poses], kDumpRows rows per tile) or nullptr
+    int dump_all;             // 0: first tile only (debug hook)   1: every tile (training: exports for the weight gradients)
+    const float* tan_in;      // MODE 2: tangent of the DFNet input, [tile][128][32] floats
     long long B;
     int ntiles;
     int steps;                // projection steps fused in this launch (>=1)
@@ -689,8 +691,12 @@ __device__ __forceinline__ void aa_to_quat_vjp(const float (&a)[3], const float 
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <bool kGrad>
+// MODE 0: forward only.  MODE 1: forward + reverse (+ step).  MODE 2: forward, then the forward-mode tangent of the
+// DFNet along a given input tangent (same weights, activation replaced by a multiply with the stored derivative) --
+// the second launch of a training step (Eikonal term), see posendf_b200/train.py.
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p) {
+    constexpr bool kGrad = (MODE == 1);
     extern __shared__ __align__(1024) uint8_t smem[];
     float* X = reinterpret_cast<float*>(smem + kSmX);
     float* Y = reinterpret_cast<float*>(smem + kSmY);
@@ -721,6 +727,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     const int fwd_slabs = p.f0_slabs + kS1 + 4 * kS23 + kS4 + kS5;
     constexpr int bwd_slabs = kSB5 + kS1 + 4 * kS23 + kS4 + kSB0;
     const int step_slabs = fwd_slabs + (kGrad ? bwd_slabs : 0);
+    constexpr int kPasses = (MODE == 2) ? 2 : 1;   // MODE 2 replays the forward slab stream for the tangent pass
 
     // ------------------------------------------------------------------ compute warps
     Ctx c;
@@ -730,7 +737,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     c.ng2 = (warp & 3) * 8 + (lane & 7); c.kg = warp >> 2;
     c.df_act = p.df_act; c.df_beta = p.df_beta; c.df_inv_beta = 1.0f / p.df_beta;
     c.dscr = p.dscratch ? p.dscratch + (size_t)blockIdx.x * kUnits * 32 : nullptr;
-    const bool keep = kGrad;
+    const bool keep = (MODE >= 1);
     EncLane enc;
     enc.l = lane & 7; enc.base = lane & 24; enc.m = warp * 4 + (lane >> 3);
     Pipe pipe;
@@ -739,7 +746,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     pipe.wsrc = reinterpret_cast<const char*>(p.wstream) + (size_t)warp * kSlabBytes;
     {
         const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        pipe.left = (uint32_t)my_tiles * (uint32_t)p.steps * (uint32_t)step_slabs;
+        pipe.left = (uint32_t)my_tiles * (uint32_t)p.steps * (uint32_t)step_slabs * (uint32_t)kPasses;
         pipe.pos = 0;
         // prologue: fill both stages of this warp's ring
         refill(pipe, c, 0);
@@ -749,7 +756,8 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const long long pose0 = (long long)tile * kTileM;
         const int nvalid = (int)min((long long)kTileM, p.B - pose0);
-        float* dbg = (tile == 0) ? p.dbg : nullptr;
+        float* dbg = (p.dbg == nullptr) ? nullptr
+                     : (p.dump_all ? p.dbg + (size_t)tile * kDumpRows * 32 : (tile == 0 ? p.dbg : nullptr));
 
         // ---- load the pose tile (coalesced), zero-fill the tail
         if (p.input_kind == IN_QUAT) {
@@ -805,62 +813,70 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 }
             }
             gemm_bar();
-            dump_rows(dbg_s, 0, X, p.z0_rows, tid);
+            for (int pass = 0; pass < kPasses; ++pass) {
+            const bool tangent = (MODE == 2) && (pass == 1);
+            float* dbg_p = (MODE == 2) ? (tangent ? dbg_s : nullptr) : dbg_s;
+            if (tangent) {   // the DFNet input tangent replaces z0; every op below becomes linear (no bias, act -> act')
+                const float* src = p.tan_in + (size_t)tile * 128 * 32;
+                for (int idx = tid; idx < p.z0_rows * 32; idx += kGemmThreads) X[swz(idx >> 5, idx & 31)] = __ldg(src + idx);
+                gemm_bar();
+            }
+            dump_rows(dbg_p, 0, X, p.z0_rows, tid);
 
             // ================================================================= forward
             {   // F0: z0 (X) -> z1 (Y), 256 wide
                 float acc[8][8];
-                if (c.kg == 0) acc_init_bias<8, 2>(acc, p.bias[0], c.ng2, 256); else acc_zero<8>(acc);
+                if (c.kg == 0 && !tangent) acc_init_bias<8, 2>(acc, p.bias[0], c.ng2, 256); else acc_zero<8>(acc);
                 gemm_op<8, 2>(acc, X, p.f0_slabs, pipe, c);
                 splitk_combine<8>(acc, Y, c);
-                if (c.kg == 0) epilogue_fwd<8, 2>(acc, Y, kU1, c, keep);
+                if (c.kg == 0) { if (!tangent) epilogue_fwd<8, 2>(acc, Y, kU1, c, keep); else epilogue_bwd<8, 2>(acc, Y, kU1, c); }
             }
             gemm_bar();
-            dump_rows(dbg_s, 128, Y, 256, tid);
+            dump_rows(dbg_p, 128, Y, 256, tid);
             {   // F1: z1 (Y) -> z2 (X), 512 wide
                 float acc[8][8];
-                acc_init_bias<8>(acc, p.bias[1], c.ng, 512);
+                if (!tangent) acc_init_bias<8>(acc, p.bias[1], c.ng, 512); else acc_zero<8>(acc);
                 gemm_op<8>(acc, Y, kS1, pipe, c);
-                epilogue_fwd<8>(acc, X, kU2, c, keep);
+                if (!tangent) epilogue_fwd<8>(acc, X, kU2, c, keep); else epilogue_bwd<8>(acc, X, kU2, c);
             }
             gemm_bar();
-            dump_rows(dbg_s, 384, X, 512, tid);
+            dump_rows(dbg_p, 384, X, 512, tid);
             {   // F2/F3 fused: z3 chunk (Y) is consumed at once as a K-chunk of layer 3; z4 -> X
                 float acc3[8][8];
-                acc_init_bias<8>(acc3, p.bias[3], c.ng, 512);
+                if (!tangent) acc_init_bias<8>(acc3, p.bias[3], c.ng, 512); else acc_zero<8>(acc3);
                 for (int ch = 0; ch < 2; ++ch) {
                     float acc2[8][8];
-                    acc_init_bias<8>(acc2, p.bias[2] + ch * 512, c.ng, 512);
+                    if (!tangent) acc_init_bias<8>(acc2, p.bias[2] + ch * 512, c.ng, 512); else acc_zero<8>(acc2);
                     gemm_op<8>(acc2, X, kS23, pipe, c);
-                    epilogue_fwd<8>(acc2, Y, kU3 + ch * 512, c, keep);
+                    if (!tangent) epilogue_fwd<8>(acc2, Y, kU3 + ch * 512, c, keep); else epilogue_bwd<8>(acc2, Y, kU3 + ch * 512, c);
                     gemm_bar();
-                    dump_rows(dbg_s, 896 + ch * 512, Y, 512, tid);
+                    dump_rows(dbg_p, 896 + ch * 512, Y, 512, tid);
                     gemm_op<8>(acc3, Y, kS23, pipe, c);
                     gemm_bar();
                 }
-                epilogue_fwd<8>(acc3, X, kU4, c, keep);
+                if (!tangent) epilogue_fwd<8>(acc3, X, kU4, c, keep); else epilogue_bwd<8>(acc3, X, kU4, c);
             }
             gemm_bar();
-            dump_rows(dbg_s, 1920, X, 512, tid);
+            dump_rows(dbg_p, 1920, X, 512, tid);
             {   // F4: z4 (X) -> z5 (Y), 256 wide
                 float acc[8][8];
-                if (c.kg == 0) acc_init_bias<8, 2>(acc, p.bias[4], c.ng2, 256); else acc_zero<8>(acc);
+                if (c.kg == 0 && !tangent) acc_init_bias<8, 2>(acc, p.bias[4], c.ng2, 256); else acc_zero<8>(acc);
                 gemm_op<8, 2>(acc, X, kS4, pipe, c);
                 splitk_combine<8>(acc, Y, c);
-                if (c.kg == 0) epilogue_fwd<8, 2>(acc, Y, kU5, c, keep);
+                if (c.kg == 0) { if (!tangent) epilogue_fwd<8, 2>(acc, Y, kU5, c, keep); else epilogue_bwd<8, 2>(acc, Y, kU5, c); }
             }
             gemm_bar();
-            dump_rows(dbg_s, 2432, Y, 256, tid);
+            dump_rows(dbg_p, 2432, Y, 256, tid);
             {   // F5: z5 (Y) -> z6 (X), 64 wide
                 float acc[8][1];
-                acc_init_bias<1>(acc, p.bias[5], c.ng, 64);
+                if (!tangent) acc_init_bias<1>(acc, p.bias[5], c.ng, 64); else acc_zero<1>(acc);
                 gemm_op<1>(acc, Y, kS5, pipe, c);
-                epilogue_fwd<1>(acc, X, kU6, c, keep);
+                if (!tangent) epilogue_fwd<1>(acc, X, kU6, c, keep); else epilogue_bwd<1>(acc, X, kU6, c);
             }
             gemm_bar();
-            dump_rows(dbg_s, 2688, X, 64, tid);
+            dump_rows(dbg_p, 2688, X, 64, tid);
             // L6 (64 -> 1) + output activation: 8 lanes per pose, shuffle reduction
-            {
+            if (!tangent) {
                 const int m = enc.m;
                 float s = 0.0f;
 #pragma unroll
@@ -879,6 +895,8 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                     if (p.dist != nullptr && m < nvalid && st == p.steps - 1) p.dist[pose0 + m] = d;
                 }
             }
+            if (MODE == 2) gemm_bar();   // X (z6 / its tangent) is reloaded by the next pass
+            }  // passes
             if (!kGrad) {
                 gemm_bar();
                 continue;

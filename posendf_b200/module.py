@@ -16,9 +16,10 @@ The parameter-holding submodules (StructureEncoder / BoneMLP / DFNet) exist so t
 load_state_dict(), parameters() and .to() behave as in the reference; the packed device copy of the weights
 inside the engine is a cache that is rebuilt whenever a parameter tensor changes version.
 
-train=True (model/posendf.py:78-99: dist + manifold + Eikonal losses, needs d/dtheta and a double backward)
-is NOT part of the fused path yet; it is served by plain torch autograd over the same
-submodules on the GPU and documented as such in DESIGN.md.
+train=True (model/posendf.py:78-99: dist + manifold + Eikonal losses and their parameter gradients, including the
+Eikonal double backward) runs on the fused path too: posendf_b200/train.py (three fused launches exporting the
+operands of the weight-gradient GEMMs, cuBLAS for those batch reductions, torch autograd only for the 3 516-parameter
+encoder).  opt['train']['fused_train'] = False selects plain torch autograd over the same submodules instead.
 """
 from __future__ import annotations
 
@@ -129,6 +130,8 @@ class PoseNDF(nn.Module):
                          enc_beta=float(m["StrEnc"].get("beta", 100.0)), df_act=m["DFNet"]["act"],
                          df_beta=float(m["DFNet"].get("beta", 100.0)), in_dim=int(m["DFNet"]["in_dim"]),
                          dims=tuple(int(d) for d in m["DFNet"]["dims"]))
+        # train=True: fused-kernel path (posendf_b200/train.py); set opt['train']['fused_train']=False for plain torch autograd
+        self._fused_train = bool(opt["train"].get("fused_train", True))
         self._engine = None
         self._engine_key = None
         self._weights_sig = None
@@ -218,6 +221,11 @@ class PoseNDF(nn.Module):
     def forward(self, pose, dist_gt=None, man_poses=None, train=True, eikonal=0.0):
         if not train:
             return {"dist_pred": self.distance(pose)}
+        if self._fused_train and next(self.parameters()).is_cuda:
+            from .train import train_forward
+            pose = pose.to(device=self.device).reshape(-1, 21, 4)
+            pose.requires_grad = True                      # the reference does this in place (model/posendf.py:66)
+            return train_forward(self, pose.detach(), dist_gt, man_poses, eikonal)
         return self._train_forward(pose, dist_gt, man_poses, eikonal)
 
     def _train_forward(self, pose, dist_gt, man_poses, eikonal):

@@ -1,0 +1,266 @@
+"""Training step of the reference (model/posendf.py:78-99 losses, model/train_posendf.py:93-99 backward) on top of
+the fused kernel.
+
+    L = w_d * L1|L2(d(x), d_gt) + w_m * mean|d(x_man)| + w_e * mean_{b,j} (|g_{b,j}| - 1)^2 ,   g = d d / d x
+
+What runs where
+  * fused sm_100a kernel (libpndf):  d, g and -- exported per 32-pose tile -- every layer input z_l and every
+    pre-activation adjoint  a_l = d d / d pre_l  (launch 1, also for the manifold batch without normalisation), and
+    the forward-mode tangents  zdot_l  of all layer inputs along a given input tangent (launch 2, Eikonal term).
+    That is 99.8 % of the per-sample arithmetic (the 7-layer DFNet chain, three times).
+  * cuBLAS through torch.mm (plain library GEMMs, fp32):  the batch reductions
+        dW_l = sum_b  a_l[b] (x) (delta_b z_l[b] + zdot_l[b])   (+ second-order term for softplus)
+  * torch autograd on the 3 516-parameter encoder only (0.2 % of the arithmetic): its parameter gradients, given the
+    upstream gradients on its output that the kernel produced, and the input tangent of launch 2 (torch.func.jvp).
+
+Eikonal term.  With v = dE/dg held fixed, dE/dtheta = d/dtheta <v, g(theta)> = d/dtheta (JVP of d along v).  The
+tangent network has the same linear structure as the linearised primal, so for layer l
+        dE/dW_l = sum_b  a_l[b] (x) zdot_l[b]  +  pbar_l[b] (x) z_l[b] ,
+where pbar_l is the second-order adjoint:  pbar_l = zbar_{l+1} * phi'(pre_l) + gbar_{l+1} * phi''(pre_l) * pdot_l,
+zbar_l = W_l^T pbar_l.  phi'' == 0 for relu / lrelu (pbar vanishes, one extra launch is all it takes); for softplus
+phi'' = beta phi' (1 - phi') and the pbar chain is evaluated here with seven cuBLAS GEMMs on the exported tensors.
+
+Everything is checked against the reference's own autograd (fp64 golden gradients) in tests/test_gpu_train.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+from torch.func import functional_call, jvp
+
+from . import _lib
+
+DUMP_ROWS = 5504
+# layer inputs z_0..z_6: (row offset, width); z_0 is 126 wide with the encoder, 84 without (rows padded to 128)
+Z_ROWS = [(0, None), (128, 256), (384, 512), (896, 1024), (1920, 512), (2432, 256), (2688, 64)]
+# adjoints of the pre-activations pre_0..pre_5 (pre_l feeds z_{l+1}); pre_6 is the scalar s
+A_ROWS = [(5120, 256), (4608, 512), (3584, 1024), (3072, 512), (2816, 256), (2752, 64)]
+G0_ROW = 5376
+CHUNK = 16384      # poses per export chunk (bounds the dump buffers at ~350 MB each)
+
+
+def _rows(dump, r0, n, B):
+    """dump (T, 5504, 32) -> (B, n) matrix of rows [r0, r0+n)"""
+    return dump[:, r0:r0 + n, :].permute(0, 2, 1).reshape(-1, n)[:B]
+
+
+def _pack_tangent(zdot, z0_rows):
+    """(B, w) tangent of the DFNet input -> [tile][128][32] floats"""
+    B, w = zdot.shape
+    T = (B + 31) // 32
+    buf = torch.zeros(T * 32, 128, device=zdot.device, dtype=torch.float32)
+    buf[:B, :w] = zdot
+    return buf.reshape(T, 32, 128).permute(0, 2, 1).contiguous()
+
+
+class _Exports:
+    def __init__(self, eng, x, normalise):
+        B = x.shape[0]
+        T = (B + 31) // 32
+        self.B = B
+        self.dump = torch.empty(T, DUMP_ROWS, 32, device=x.device, dtype=torch.float32)
+        self.dist = torch.empty(B, 1, device=x.device, dtype=torch.float32)
+        self.grad = torch.empty(B, 21, 4, device=x.device, dtype=torch.float32)
+        _lib.check(eng.lib.pndf_forward_grad_export(eng._h, x.data_ptr(), B, int(normalise), self.dist.data_ptr(),
+                                                    self.grad.data_ptr(), self.dump.data_ptr(),
+                                                    torch.cuda.current_stream(x.device).cuda_stream))
+
+    def z(self, l, in_dim):
+        r0, n = Z_ROWS[l]
+        return _rows(self.dump, r0, in_dim if l == 0 else n, self.B)
+
+    def a(self, l):
+        r0, n = A_ROWS[l]
+        return _rows(self.dump, r0, n, self.B)
+
+    def g0(self, in_dim):
+        return _rows(self.dump, G0_ROW, in_dim, self.B)
+
+
+def _tangent_exports(eng, x, normalise, zdot0):
+    B = x.shape[0]
+    T = (B + 31) // 32
+    dump = torch.empty(T, DUMP_ROWS, 32, device=x.device, dtype=torch.float32)
+    tan = _pack_tangent(zdot0, 128)
+    _lib.check(eng.lib.pndf_forward_tangent_export(eng._h, x.data_ptr(), B, int(normalise), tan.data_ptr(), dump.data_ptr(),
+                                                   torch.cuda.current_stream(x.device).cuda_stream))
+    return dump
+
+
+def _out_act_deriv(d, act, beta):
+    """phi_out'(s) and phi_out''(s) recovered from d = phi_out(s): relu (relu / lrelu configs) or softplus(beta)."""
+    if act == "softplus":
+        sig = -torch.expm1(-beta * d)               # sigma(beta s) = 1 - exp(-beta d), accurate for tiny d
+        return sig, beta * sig * (1.0 - sig)
+    pos = (d > 0).to(d.dtype)
+    return pos, torch.zeros_like(d)
+
+
+def _hidden_act_deriv(z_next, act, beta):
+    """phi'(pre_l) and phi''(pre_l)/phi'(pre_l) recovered from z_{l+1} = phi(pre_l)."""
+    if act == "softplus":
+        sig = -torch.expm1(-beta * z_next)           # phi' = sigma(beta pre) = 1 - exp(-beta z), accurate for tiny z
+        return sig, beta * (1.0 - sig)
+    slope = 0.0 if act == "relu" else 0.01
+    return torch.where(z_next > 0, torch.ones_like(z_next), torch.full_like(z_next, slope)), None
+
+
+def _encoder_fn(net, normalise):
+    names = [n for n, _ in net.enc.named_parameters()] if net.enc is not None else []
+    params = {n: p for n, p in net.enc.named_parameters()} if net.enc is not None else {}
+
+    def f(x, ps):
+        q = F.normalize(x, dim=1) if normalise else x
+        if net.enc is None:
+            return q.reshape(len(q), -1)
+        return functional_call(net.enc, ps, (q,))
+    return f, names, params
+
+
+def _accumulate(acc, name, val):
+    acc[name] = val if name not in acc else acc[name] + val
+
+
+def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_norm=None):
+    """Parameter gradients of  sum_b delta[b] * d(x[b])  (+ those of the Eikonal term if eik_weight is not None), the
+    distances and the Eikonal value.  x (B,21,4) fp32 CUDA; delta_fn(dist_chunk, lo, hi) -> (hi-lo,) upstream gradient
+    on d for poses [lo,hi) (evaluated after the distances are known, so no extra forward launch is needed).  Returns
+    (grads_first: dict name->tensor, grads_eik: dict or None, dist (B,1), eikonal scalar or None)."""
+    eng = net.engine()
+    cfg = net._cfg
+    in_dim, act, beta = cfg["in_dim"], cfg["df_act"], cfg["df_beta"]
+    W = [getattr(net.dfnet, f"lin{l}").weight.detach() for l in range(7)]
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        g1, ge = {}, ({} if eik_weight is not None else None)
+        dists, eik_sum = [], x.new_zeros(())
+        Btot = x.shape[0]
+        enc_f, enc_names, enc_params = _encoder_fn(net, normalise)
+        for c0 in range(0, Btot, CHUNK):
+            xc = x[c0:c0 + CHUNK].contiguous()
+            ex = _Exports(eng, xc, normalise)
+            dists.append(ex.dist)
+            dl = delta_fn(ex.dist, c0, c0 + xc.shape[0]).reshape(-1, 1)
+            gs, gss = _out_act_deriv(ex.dist, act, beta)                    # (B,1)
+            A = [ex.a(l) for l in range(6)]
+            Z = [ex.z(l, in_dim) for l in range(7)]
+            # ---- first-order term: dW_l = (delta * a_l)^T z_l
+            for l in range(6):
+                da = dl * A[l]
+                _accumulate(g1, f"dfnet.lin{l}.weight", da.t() @ Z[l])
+                _accumulate(g1, f"dfnet.lin{l}.bias", da.sum(0))
+            _accumulate(g1, "dfnet.lin6.weight", ((dl * gs) * Z[6]).sum(0, keepdim=True))
+            _accumulate(g1, "dfnet.lin6.bias", (dl * gs).sum(0))
+            up0 = dl * ex.g0(in_dim)                                         # upstream on the encoder output
+            if net.enc is not None:
+                with torch.enable_grad():
+                    z0 = enc_f(xc, enc_params)
+                    gps = torch.autograd.grad(z0, list(enc_params.values()), up0)
+                for n, gp in zip(enc_names, gps):
+                    _accumulate(g1, "enc." + n, gp)
+            if eik_weight is None:
+                continue
+            # ---- Eikonal term
+            g = ex.grad
+            nrm = g.norm(2, dim=-1, keepdim=True)
+            count = float((loss_norm if loss_norm is not None else Btot) * 21)
+            eik_sum = eik_sum + ((nrm - 1) ** 2).sum()
+            v = (2.0 * (nrm - 1) / count) * (g / nrm)                        # dE/dg  (mean over all (b,j))
+            with torch.enable_grad():
+                z0_e, zdot0 = jvp(lambda xx: enc_f(xx, enc_params), (xc,), (v,))
+            dump_t = _tangent_exports(eng, xc, normalise, zdot0.detach())
+            Zd = [zdot0.detach()] + [_rows(dump_t, Z_ROWS[l][0], Z_ROWS[l][1], ex.B) for l in range(1, 7)]
+            for l in range(6):
+                _accumulate(ge, f"dfnet.lin{l}.weight", A[l].t() @ Zd[l])
+            _accumulate(ge, "dfnet.lin6.weight", (gs * Zd[6]).sum(0, keepdim=True))
+            up_z0dot = ex.g0(in_dim)                                         # dE/d(zdot_0) = adjoint of z_0 (unit upstream)
+            up_z0 = None
+            if act == "softplus":
+                # second-order adjoint chain (phi'' != 0): seven GEMMs on the exported tensors
+                sdot = Zd[6] @ W[6].t()                                      # (B,1)
+                pbar = gss * sdot                                            # adjoint of s
+                _accumulate(ge, "dfnet.lin6.weight", (pbar * Z[6]).sum(0, keepdim=True))
+                _accumulate(ge, "dfnet.lin6.bias", pbar.sum(0))
+                zbar = pbar @ W[6]                                           # (B,64) adjoint of z_6
+                for l in range(5, -1, -1):
+                    d1, ratio = _hidden_act_deriv(Z[l + 1], act, beta)       # phi'(pre_l), phi''/phi'
+                    pdot = Zd[l + 1] / d1.clamp_min(1e-30)                   # tangent of pre_l
+                    pbar = zbar * d1 + A[l] * ratio * pdot                   # A[l] = gbar_{l+1} * phi'
+                    _accumulate(ge, f"dfnet.lin{l}.weight", pbar.t() @ Z[l])
+                    _accumulate(ge, f"dfnet.lin{l}.bias", pbar.sum(0))
+                    zbar = pbar @ W[l]
+                up_z0 = zbar
+            if net.enc is not None:
+                with torch.enable_grad():
+                    obj = (zdot0 * up_z0dot).sum()
+                    if up_z0 is not None:
+                        obj = obj + (z0_e * up_z0).sum()
+                    gps = torch.autograd.grad(obj, list(enc_params.values()), allow_unused=True)
+                for n, gp in zip(enc_names, gps):
+                    if gp is not None:
+                        _accumulate(ge, "enc." + n, gp)
+        dist = torch.cat(dists, 0)
+        eik = None
+        if eik_weight is not None:
+            eik = eik_sum / float((loss_norm if loss_norm is not None else Btot) * 21)
+        return g1, ge, dist, eik
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+
+
+class FusedTrainLosses(torch.autograd.Function):
+    """(dist loss, manifold loss, Eikonal loss) of model/posendf.py:85-96 with parameter gradients from the fused path.
+    backward() combines the three per-term gradient sets with the upstream weights (model/train_posendf.py:95-98)."""
+
+    @staticmethod
+    def forward(ctx, net, pose, dist_gt, man_poses, loss_type, want_eik, *params):
+        names = [n for n, _ in net.named_parameters()]
+        B = pose.shape[0]
+
+        def delta_dist(dist, lo, hi):
+            diff = dist[:, 0] - dist_gt[lo:hi]
+            return torch.sign(diff) / B if loss_type == "l1" else 2.0 * diff / B
+
+        g_dist, g_eik, d, eik = fused_param_grads(net, pose, delta_dist, True, 1.0 if want_eik else None)
+        diff = d[:, 0] - dist_gt
+        loss_d = diff.abs().mean() if loss_type == "l1" else (diff * diff).mean()
+        g_man, loss_m = {}, loss_d.new_zeros(())
+        if want_eik:     # the reference only reports / trains the manifold term together with the Eikonal term (posendf.py:94-99)
+            Bm = man_poses.shape[0]
+            g_man, _, dm, _ = fused_param_grads(net, man_poses, lambda dist, lo, hi: torch.sign(dist[:, 0]) / Bm, False, None)
+            loss_m = dm.abs().mean()
+        ctx.grads = [[gd.get(n) for n in names] for gd in (g_dist, g_man, g_eik if g_eik is not None else {})]
+        ctx.shapes = [p.shape for p in params]
+        if not want_eik:
+            eik = loss_d.new_zeros(())
+        return loss_d, loss_m, eik
+
+    @staticmethod
+    def backward(ctx, gd, gm, ge):
+        out = []
+        for i, shp in enumerate(ctx.shapes):
+            tot = None
+            for up, gset in zip((gd, gm, ge), ctx.grads):
+                gi = gset[i]
+                if gi is None or up is None:
+                    continue
+                term = up * gi.reshape(shp)
+                tot = term if tot is None else tot + term
+            out.append(tot)
+        return (None, None, None, None, None, None, *out)
+
+
+def train_forward(net, pose, dist_gt, man_poses, eikonal):
+    """PoseNDF.forward(train=True) on the fused path: returns (loss, dict) exactly like model/posendf.py:97-99."""
+    dev = next(net.parameters()).device
+    x = pose.to(dev).reshape(-1, 21, 4).float().contiguous()
+    gt = dist_gt.to(dev).reshape(-1).float()
+    man = man_poses.to(dev).reshape(-1, 21, 4).float().contiguous()
+    params = list(net.parameters())
+    loss_d, loss_m, eik = FusedTrainLosses.apply(net, x, gt, man, net.loss, eikonal > 0.0, *params)
+    if eikonal > 0.0:
+        return loss_d, {"dist": loss_d, "man_loss": loss_m, "eikonal": eik}
+    return loss_d, {"dist": loss_d}

@@ -1,0 +1,102 @@
+"""GPU: training step on the fused path (posendf_b200/train.py) against the reference's own autograd
+(oracle/posendf_torch.py, pinned to the reference's golden gradients in tests/test_oracle.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import case_cfg, load_golden
+from oracle import posendf_torch as otorch
+from posendf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _opt(cfg, loss="l1", fused=True):
+    return {"train": {"device": "cuda", "loss_type": loss, "batch_size": 4, "fused_train": fused},
+            "model": {"StrEnc": {"use": cfg["use_enc"], "act": cfg["enc_act"], "beta": cfg["enc_beta"]},
+                      "DFNet": {"in_dim": 126 if cfg["use_enc"] else 84, "dims": [256, 512, 1024, 512, 256, 64],
+                                "act": cfg["df_act"], "beta": cfg["df_beta"]}}}
+
+
+def _batch(seed, B):
+    tp = synth.make_poses(2000 + seed, B, kind="noisy", sigma=0.25)
+    tm = synth.make_poses(3000 + seed, B, kind="randn")
+    tgt = (synth.uniform01(4000 + seed, B) * 0.5).astype(np.float32)
+    return tp, tgt, tm
+
+
+@pytest.mark.parametrize("name,B", [("lrelu_enc_s1", 96), ("relu_enc_s2", 70), ("softplus_enc_s3", 96),
+                                    ("softplus_b5_enc_s4", 64), ("lrelu_enc_l2_s8", 64), ("mixed_relu_softplus_s7", 64)])
+def test_train_losses_and_parameter_gradients_vs_reference_autograd(name, B):
+    from posendf_b200 import PoseNDF
+    meta, _ = load_golden(name)
+    cfg = case_cfg(meta)
+    loss_type = meta.get("loss_type", "l1")
+    params = synth.make_params(meta["seed"], sensitised=meta["sensitised"])
+    net = PoseNDF(_opt(cfg, loss_type))
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    net.train()
+    tp, tgt, tm = _batch(meta["seed"], B)
+    weights = {"dist": 1.0, "man_loss": 0.7, "eikonal": 1.3}
+    net.zero_grad()
+    loss, ld = net(torch.from_numpy(tp), torch.from_numpy(tgt), torch.from_numpy(tm), train=True, eikonal=1.0)
+    assert set(ld) == {"dist", "man_loss", "eikonal"} and loss is ld["dist"]
+    sum(weights[k] * v for k, v in ld.items()).backward()
+    # oracle: the reference's computation in fp64
+    tp64 = otorch.to_torch_params(params, torch.float64, requires_grad=True)
+    _, ld_ref, g_ref = otorch.train_step_grads(tp64, torch.from_numpy(tp).double(), torch.from_numpy(tgt).double(),
+                                                torch.from_numpy(tm).double(), cfg, weights=weights, loss_type=loss_type)
+    for k in ("dist", "man_loss", "eikonal"):
+        assert abs(ld[k].item() - ld_ref[k].item()) < 2e-5 * max(1.0, abs(ld_ref[k].item())), k
+    worst = 0.0
+    for n, p in net.named_parameters():
+        ref = g_ref[n].numpy()
+        got = p.grad.cpu().numpy().astype(np.float64)
+        err = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-12)
+        worst = max(worst, err)
+        # kink flips (relu/lrelu) perturb single samples; norm-wise 5e-3 per tensor, most are ~1e-6
+        assert err < (5e-3 if cfg["df_act"] != "softplus" else 2e-4), (n, err)
+    print(name, "worst per-tensor relative gradient error", worst)
+
+
+def test_eikonal_off_returns_dist_only_and_matches():
+    from posendf_b200 import PoseNDF
+    meta, _ = load_golden("lrelu_enc_s1")
+    cfg = case_cfg(meta)
+    params = synth.make_params(1)
+    net = PoseNDF(_opt(cfg))
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    tp, tgt, tm = _batch(1, 64)
+    loss, ld = net(torch.from_numpy(tp), torch.from_numpy(tgt), torch.from_numpy(tm), train=True, eikonal=0.0)
+    assert set(ld) == {"dist"}
+    loss.backward()
+    tp64 = otorch.to_torch_params(params, torch.float64, requires_grad=True)
+    tot, _, g_ref = otorch.train_step_grads(tp64, torch.from_numpy(tp).double(), torch.from_numpy(tgt).double(),
+                                             torch.from_numpy(tm).double(), cfg, weights={"dist": 1.0}, eikonal=0.0)
+    assert abs(loss.item() - tot.item()) < 1e-5
+    for n, p in net.named_parameters():
+        ref = g_ref[n].numpy()
+        assert np.linalg.norm(p.grad.cpu().numpy() - ref) < 5e-3 * max(np.linalg.norm(ref), 1e-12), n
+
+
+def test_fused_train_step_equals_torch_autograd_path_and_adam_step_runs():
+    """one trainer step (model/train_posendf.py:93-99) on both paths from the same init: losses and gradient norm agree."""
+    from posendf_b200 import PoseNDF
+    meta, _ = load_golden("softplus_enc_s3")
+    cfg = case_cfg(meta)
+    params = synth.make_params(3)
+    tp, tgt, tm = _batch(3, 128)
+    outs = []
+    for fused in (True, False):
+        net = PoseNDF(_opt(cfg, fused=fused))
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+        opt = torch.optim.Adam(net.parameters(), lr=1e-5, weight_decay=1e-4)
+        opt.zero_grad()
+        _, ld = net(torch.from_numpy(tp), torch.from_numpy(tgt), torch.from_numpy(tm), train=True, eikonal=1.0)
+        sum(ld.values()).backward()
+        gn = torch.sqrt(sum((p.grad ** 2).sum() for p in net.parameters())).item()
+        opt.step()
+        outs.append((gn, {k: v.item() for k, v in ld.items()}))
+    assert abs(outs[0][0] - outs[1][0]) < 1e-3 * outs[1][0]
+    for k in outs[0][1]:
+        assert abs(outs[0][1][k] - outs[1][1][k]) < 1e-5 * max(1.0, abs(outs[1][1][k]))
