@@ -38,7 +38,7 @@ Z_ROWS = [(0, None), (128, 256), (384, 512), (896, 1024), (1920, 512), (2432, 25
 # adjoints of the pre-activations pre_0..pre_5 (pre_l feeds z_{l+1}); pre_6 is the scalar s
 A_ROWS = [(5120, 256), (4608, 512), (3584, 1024), (3072, 512), (2816, 256), (2752, 64)]
 G0_ROW = 5376
-CHUNK = 16384      # poses per export chunk (bounds the dump buffers at ~350 MB each)
+CHUNK = 65536      # poses per export chunk (bounds the dump buffers at ~1.4 GB each)
 
 
 def _rows(dump, r0, n, B):
@@ -155,13 +155,13 @@ def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_no
             _accumulate(g1, "dfnet.lin6.weight", ((dl * gs) * Z[6]).sum(0, keepdim=True))
             _accumulate(g1, "dfnet.lin6.bias", (dl * gs).sum(0))
             up0 = dl * ex.g0(in_dim)                                         # upstream on the encoder output
-            if net.enc is not None:
-                with torch.enable_grad():
-                    z0 = enc_f(xc, enc_params)
-                    gps = torch.autograd.grad(z0, list(enc_params.values()), up0)
-                for n, gp in zip(enc_names, gps):
-                    _accumulate(g1, "enc." + n, gp)
             if eik_weight is None:
+                if net.enc is not None:
+                    with torch.enable_grad():
+                        z0 = enc_f(xc, enc_params)
+                        gps = torch.autograd.grad(z0, list(enc_params.values()), up0)
+                    for n, gp in zip(enc_names, gps):
+                        _accumulate(g1, "enc." + n, gp)
                 continue
             # ---- Eikonal term
             g = ex.grad
@@ -194,14 +194,19 @@ def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_no
                     zbar = pbar @ W[l]
                 up_z0 = zbar
             if net.enc is not None:
+                # two reverse sweeps over ONE (jvp-augmented) encoder graph: first-order term and Eikonal term
                 with torch.enable_grad():
-                    obj = (zdot0 * up_z0dot).sum()
+                    obj1 = (z0_e * up0).sum()
+                    obj2 = (zdot0 * up_z0dot).sum()
                     if up_z0 is not None:
-                        obj = obj + (z0_e * up_z0).sum()
-                    gps = torch.autograd.grad(obj, list(enc_params.values()), allow_unused=True)
-                for n, gp in zip(enc_names, gps):
-                    if gp is not None:
-                        _accumulate(ge, "enc." + n, gp)
+                        obj2 = obj2 + (z0_e * up_z0).sum()
+                    plist = list(enc_params.values())
+                    gp1 = torch.autograd.grad(obj1, plist, retain_graph=True)
+                    gp2 = torch.autograd.grad(obj2, plist, allow_unused=True)
+                for n, a1, a2 in zip(enc_names, gp1, gp2):
+                    _accumulate(g1, "enc." + n, a1)
+                    if a2 is not None:
+                        _accumulate(ge, "enc." + n, a2)
         dist = torch.cat(dists, 0)
         eik = None
         if eik_weight is not None:
