@@ -125,6 +125,19 @@ int pndf_forward_grad_export(pndf_handle* h, const float* pose_dev, int64_t B, i
 int pndf_forward_tangent_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, const float* tan_dev,
                                 float* dump_dev, void* stream);
 
+/* Structure-encoder side of the training step (model/network/net_modules.py:140-170, 3 516 parameters).
+ * pndf_encoder_tangent: tangent of the encoder output (or of the normalised pose without encoder) along the pose
+ *   tangent v_dev (B*84), written as the [tile][128][32] input of pndf_forward_tangent_export.
+ * pndf_encoder_param_grads: parameter gradients (reference order, 3 516 floats per set) of
+ *     set 0:  sum_b <up_first[b], z0[b]>                      set 1:  sum_b <up_tangent[b], zdot0[b]> + <up_second[b], z0[b]>
+ *   into grads_dev[2][3516] (zeroed here; any of the three upstream arrays (B*126) may be NULL), including the
+ *   second-derivative terms of a softplus encoder. */
+int pndf_encoder_tangent(pndf_handle* h, const float* pose_dev, const float* v_dev, int64_t B, int normalise,
+                         float* zdot_tiles_dev, void* stream);
+int pndf_encoder_param_grads(pndf_handle* h, const float* pose_dev, const float* v_dev, int64_t B, int normalise,
+                             const float* up_first_dev, const float* up_tangent_dev, const float* up_second_dev,
+                             float* grads_dev, void* stream);
+
 /* Measurement helpers used by bench.py (not on the data path):
  *   pndf_fp32_peak: in-process FFMA micro-benchmark, dense fp32 FMA TFLOP/s of this GPU right now.
  *     variant 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2).

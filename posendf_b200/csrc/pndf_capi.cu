@@ -3,6 +3,7 @@
 #include "../../include/pndf.h"
 #include "pndf_kernel.cuh"
 #include "pndf_denoise.cuh"
+#include "pndf_encoder_train.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -415,6 +416,43 @@ int pndf_forward_tangent_export(pndf_handle* h, const float* pose_dev, int64_t B
     p.pose_in = pose_dev; p.B = B; p.steps = 1; p.normalise = normalise; p.input_kind = IN_QUAT;
     p.dbg = dump_dev; p.dump_all = 1; p.tan_in = tan_dev;
     return launch(h, p, 2, (cudaStream_t)stream);
+}
+
+int pndf_encoder_tangent(pndf_handle* h, const float* pose_dev, const float* v_dev, int64_t B, int normalise,
+                         float* zdot_tiles_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (B == 0) return 0;
+    if (B < 0 || !pose_dev || !v_dev || !zdot_tiles_dev) return fail("null argument");
+    if (!h->have_weights) return fail("pndf_set_weights has not been called");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    EncTrainParams p{};
+    p.x = pose_dev; p.v = v_dev; p.encw = h->d_small + h->off_enc; p.zdot_tiles = zdot_tiles_dev; p.B = B;
+    p.normalise = normalise; p.act = h->cfg.enc_act; p.beta = h->cfg.enc_beta; p.use_enc = h->cfg.use_enc;
+    enc_tangent_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int pndf_encoder_param_grads(pndf_handle* h, const float* pose_dev, const float* v_dev, int64_t B, int normalise,
+                             const float* up_first_dev, const float* up_tangent_dev, const float* up_second_dev,
+                             float* grads_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (!h->cfg.use_enc) return fail("this configuration has no structure encoder");
+    if (B < 0 || !pose_dev || !grads_dev) return fail("null argument");
+    if (!h->have_weights) return fail("pndf_set_weights has not been called");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_OK(cudaMemsetAsync(grads_dev, 0, 2 * kEncFloats * sizeof(float), st));
+    if (B == 0) return 0;
+    EncTrainParams p{};
+    p.x = pose_dev; p.v = v_dev; p.encw = h->d_small + h->off_enc; p.up1 = up_first_dev; p.upt = up_tangent_dev;
+    p.upz = up_second_dev; p.grads = grads_dev; p.B = B; p.normalise = normalise; p.act = h->cfg.enc_act;
+    p.beta = h->cfg.enc_beta; p.use_enc = 1;
+    enc_grad_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(p);
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
 }
 
 int pndf_launch_count(pndf_handle* h, int64_t* n) {

@@ -1,0 +1,229 @@
+// pndf_encoder_train.cuh -- training-side kernels for the structure encoder (3 516 parameters, 0.2 % of the flops).
+//
+// The fused kernel leaves three per-pose vectors on the encoder output z0 (126 features):
+//     up1  = delta * dd/dz0              first-order term (dist / manifold loss)            -> gradient set 0
+//     upt  = dd/dz0                      adjoint of the TANGENT of z0 (Eikonal term)        -> gradient set 1
+//     upz  = second-order adjoint of z0  (softplus DFNet only, else null)                   -> gradient set 1
+// and the Eikonal term needs the tangent of z0 along the pose tangent v = dE/dg as the input of the tangent launch.
+// Both are one-thread-per-pose walks of the kinematic tree (reference: model/network/net_modules.py:140-170):
+//     enc_tangent_kernel : q = x/n, qdot = J_normalise v, forward + forward-mode tangent, writes zdot0 as [tile][128][32]
+//     enc_grad_kernel    : the same forward sweep, then the reverse sweep of BOTH objectives
+//                              O0 = <up1, z0>      O1 = <upt, zdot0> + <upz, z0>
+//                          including the phi'' terms of a softplus encoder, reducing the parameter gradients over the
+//                          warp with shuffles, over the block in shared memory, and over the grid with atomics.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pndf_kernel.cuh"
+
+namespace pndf {
+
+struct EncTrainParams {
+    const float* x;        // B x 84 poses
+    const float* v;        // B x 84 pose tangent (or nullptr: no tangent)
+    const float* encw;     // 3516 encoder parameters, reference order
+    const float* up1;      // B x 126 or nullptr
+    const float* upt;      // B x 126 or nullptr
+    const float* upz;      // B x 126 or nullptr
+    float* zdot_tiles;     // [tile][128][32] (tangent kernel)
+    float* grads;          // 2 x 3516 (grad kernel), accumulated with atomics: caller zeroes
+    long long B;
+    int normalise, act, use_enc;
+    float beta;
+};
+
+// value, first and second derivative of the encoder activation
+__device__ __forceinline__ void enc_act3(float s, int act, float beta, float& z, float& d1, float& d2) {
+    if (act == ACT_SOFTPLUS) {
+        z = softplus_eval(s, beta, 1.0f / beta, d1);
+        d2 = (s * beta > 20.0f) ? 0.0f : beta * d1 * (1.0f - d1);
+    } else {
+        const float slope = (act == ACT_RELU) ? 0.0f : 0.01f;
+        const bool pos = s > 0.0f;
+        z = pos ? s : s * slope;
+        d1 = pos ? 1.0f : slope;
+        d2 = 0.0f;
+    }
+}
+
+struct BoneState {
+    float u[10], ud[10];       // input and its tangent
+    float h[10], hd[10];       // hidden activation and tangent
+    float d1h[10], d2h[10];    // phi', phi'' at pre1
+    float p1d[10];             // tangent of pre1
+    float d1f[6], d2f[6];      // phi', phi'' at pre2
+    float p2d[6];              // tangent of pre2
+    float f[6], fd[6];
+};
+
+// forward + tangent of joint i for one pose; q/qd = normalised pose and tangent (84 each), feat/featd = features so far
+__device__ __forceinline__ void bone_fwd_tan(const float* __restrict__ w, int i, int par, const float* q, const float* qd,
+                                             const float (*feat)[6], const float (*featd)[6], int act, float beta, BoneState& s) {
+    const bool root = par < 0;
+    const int fin = root ? 4 : 10;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { s.u[c] = q[i * 4 + c]; s.ud[c] = qd[i * 4 + c]; }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) { s.u[4 + r] = root ? 0.0f : feat[par][r]; s.ud[4 + r] = root ? 0.0f : featd[par][r]; }
+    const float* w1 = w; const float* b1 = w + 10 * fin; const float* w2 = b1 + 10; const float* b2 = w2 + 60;
+#pragma unroll
+    for (int o = 0; o < 10; ++o) {
+        float a = __ldg(b1 + o), ad = 0.0f;
+        for (int k = 0; k < fin; ++k) { const float ww = __ldg(w1 + o * fin + k); a = fmaf(ww, s.u[k], a); ad = fmaf(ww, s.ud[k], ad); }
+        enc_act3(a, act, beta, s.h[o], s.d1h[o], s.d2h[o]);
+        s.p1d[o] = ad;
+        s.hd[o] = s.d1h[o] * ad;
+    }
+#pragma unroll
+    for (int o = 0; o < 6; ++o) {
+        float a = __ldg(b2 + o), ad = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { const float ww = __ldg(w2 + o * 10 + k); a = fmaf(ww, s.h[k], a); ad = fmaf(ww, s.hd[k], ad); }
+        enc_act3(a, act, beta, s.f[o], s.d1f[o], s.d2f[o]);
+        s.p2d[o] = ad;
+        s.fd[o] = s.d1f[o] * ad;
+    }
+}
+
+__device__ __forceinline__ void load_q_qd(const EncTrainParams& p, long long b, float* q, float* qd) {
+    float n[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float sq = 0.0f;
+        for (int j = 0; j < 21; ++j) { const float xv = p.x[b * 84 + j * 4 + c]; sq = fmaf(xv, xv, sq); }
+        n[c] = p.normalise ? fmaxf(sqrtf(sq), 1e-12f) : 1.0f;
+    }
+    for (int e = 0; e < 84; ++e) q[e] = p.x[b * 84 + e] / n[e & 3];
+    if (p.v == nullptr) {
+        for (int e = 0; e < 84; ++e) qd[e] = 0.0f;
+        return;
+    }
+    if (!p.normalise) {
+        for (int e = 0; e < 84; ++e) qd[e] = p.v[b * 84 + e];
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float dot = 0.0f;
+        for (int j = 0; j < 21; ++j) dot = fmaf(q[j * 4 + c], p.v[b * 84 + j * 4 + c], dot);
+        for (int j = 0; j < 21; ++j) qd[j * 4 + c] = (p.v[b * 84 + j * 4 + c] - q[j * 4 + c] * dot) / n[c];
+    }
+}
+
+__global__ void __launch_bounds__(128) enc_tangent_kernel(const EncTrainParams p) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    float q[84], qd[84], feat[21][6], featd[21][6];
+    load_q_qd(p, b, q, qd);
+    float* out = p.zdot_tiles + (b >> 5) * (128 * 32) + (b & 31);
+    if (!p.use_enc) {   // DFNet eats the normalised pose directly (in_dim 84): its tangent is qdot
+        for (int e = 0; e < 128; ++e) out[e * 32] = (e < 84) ? qd[e] : 0.0f;
+        return;
+    }
+    for (int i = 0; i < 21; ++i) {
+        BoneState s;
+        bone_fwd_tan(p.encw + enc_off(i), i, c_parent[i], q, qd, feat, featd, p.act, p.beta, s);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { feat[i][r] = s.f[r]; featd[i][r] = s.fd[r]; out[(i * 6 + r) * 32] = s.fd[r]; }
+    }
+    out[126 * 32] = 0.0f;
+    out[127 * 32] = 0.0f;
+}
+
+// warp-reduce v, lane 0 adds it into the block accumulator
+__device__ __forceinline__ void red_add(float* acc, float v, int lane) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) atomicAdd(acc, v);
+}
+
+__global__ void __launch_bounds__(128) enc_grad_kernel(const EncTrainParams p) {
+    __shared__ float acc[2 * kEncFloats];
+    for (int i = threadIdx.x; i < 2 * kEncFloats; i += blockDim.x) acc[i] = 0.0f;
+    __syncthreads();
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = b < p.B;
+    const long long bb = live ? b : 0;
+    const int lane = threadIdx.x & 31;
+    float q[84], qd[84], feat[21][6], featd[21][6];
+    load_q_qd(p, bb, q, qd);
+    for (int i = 0; i < 21; ++i) {
+        BoneState s;
+        bone_fwd_tan(p.encw + enc_off(i), i, c_parent[i], q, qd, feat, featd, p.act, p.beta, s);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { feat[i][r] = s.f[r]; featd[i][r] = s.fd[r]; }
+    }
+    // adjoints: set 0 = objective O0 (adjoint of f only); set 1 = objective O1 (adjoint of f and of fd)
+    float fb0[21][6], fb1[21][6], fdb1[21][6];
+    for (int i = 0; i < 21; ++i)
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const long long o = bb * 126 + i * 6 + r;
+            fb0[i][r] = (live && p.up1) ? p.up1[o] : 0.0f;
+            fb1[i][r] = (live && p.upz) ? p.upz[o] : 0.0f;
+            fdb1[i][r] = (live && p.upt) ? p.upt[o] : 0.0f;
+        }
+    for (int i = 20; i >= 0; --i) {
+        const int par = c_parent[i];
+        const bool root = par < 0;
+        const int fin = root ? 4 : 10;
+        const int off = enc_off(i);
+        const float* w1 = p.encw + off;
+        const float* w2 = w1 + 10 * fin + 10;
+        BoneState s;
+        bone_fwd_tan(p.encw + off, i, par, q, qd, feat, featd, p.act, p.beta, s);
+        float* a0 = acc + off;
+        float* a1 = acc + kEncFloats + off;
+        // layer 2
+        float p2b0[6], p2b1[6], p2db1[6];
+#pragma unroll
+        for (int o = 0; o < 6; ++o) {
+            p2b0[o] = fb0[i][o] * s.d1f[o];
+            p2db1[o] = fdb1[i][o] * s.d1f[o];
+            p2b1[o] = fb1[i][o] * s.d1f[o] + fdb1[i][o] * s.d2f[o] * s.p2d[o];
+        }
+        float hb0[10], hb1[10], hdb1[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { hb0[k] = 0.0f; hb1[k] = 0.0f; hdb1[k] = 0.0f; }
+        for (int o = 0; o < 6; ++o) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                const float ww = __ldg(w2 + o * 10 + k);
+                hb0[k] = fmaf(ww, p2b0[o], hb0[k]); hb1[k] = fmaf(ww, p2b1[o], hb1[k]); hdb1[k] = fmaf(ww, p2db1[o], hdb1[k]);
+                red_add(a0 + 10 * fin + 10 + o * 10 + k, p2b0[o] * s.h[k], lane);
+                red_add(a1 + 10 * fin + 10 + o * 10 + k, p2b1[o] * s.h[k] + p2db1[o] * s.hd[k], lane);
+            }
+            red_add(a0 + 10 * fin + 70 + o, p2b0[o], lane);
+            red_add(a1 + 10 * fin + 70 + o, p2b1[o], lane);
+        }
+        // layer 1
+        float p1b0[10], p1b1[10], p1db1[10];
+#pragma unroll
+        for (int o = 0; o < 10; ++o) {
+            p1b0[o] = hb0[o] * s.d1h[o];
+            p1db1[o] = hdb1[o] * s.d1h[o];
+            p1b1[o] = hb1[o] * s.d1h[o] + hdb1[o] * s.d2h[o] * s.p1d[o];
+        }
+        float ub0[10], ub1[10], udb1[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { ub0[k] = 0.0f; ub1[k] = 0.0f; udb1[k] = 0.0f; }
+        for (int o = 0; o < 10; ++o) {
+            for (int k = 0; k < fin; ++k) {
+                const float ww = __ldg(w1 + o * fin + k);
+                ub0[k] = fmaf(ww, p1b0[o], ub0[k]); ub1[k] = fmaf(ww, p1b1[o], ub1[k]); udb1[k] = fmaf(ww, p1db1[o], udb1[k]);
+                red_add(a0 + o * fin + k, p1b0[o] * s.u[k], lane);
+                red_add(a1 + o * fin + k, p1b1[o] * s.u[k] + p1db1[o] * s.ud[k], lane);
+            }
+            red_add(a0 + 10 * fin + o, p1b0[o], lane);
+            red_add(a1 + 10 * fin + o, p1b1[o], lane);
+        }
+        if (!root) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { fb0[par][r] += ub0[4 + r]; fb1[par][r] += ub1[4 + r]; fdb1[par][r] += udb1[4 + r]; }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * kEncFloats; i += blockDim.x) atomicAdd(p.grads + i, acc[i]);
+}
+
+}  // namespace pndf

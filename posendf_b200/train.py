@@ -10,8 +10,9 @@ What runs where
     That is 99.8 % of the per-sample arithmetic (the 7-layer DFNet chain, three times).
   * cuBLAS through torch.mm (plain library GEMMs, fp32):  the batch reductions
         dW_l = sum_b  a_l[b] (x) (delta_b z_l[b] + zdot_l[b])   (+ second-order term for softplus)
-  * torch autograd on the 3 516-parameter encoder only (0.2 % of the arithmetic): its parameter gradients, given the
-    upstream gradients on its output that the kernel produced, and the input tangent of launch 2 (torch.func.jvp).
+  * two small one-thread-per-pose kernels for the 3 516-parameter structure encoder (0.2 % of the arithmetic):
+    pndf_encoder_tangent (input tangent of launch 2) and pndf_encoder_param_grads (reverse sweep of the encoder for
+    the first-order and the Eikonal objective incl. the softplus second-derivative terms).  No torch autograd anywhere.
 
 Eikonal term.  With v = dE/dg held fixed, dE/dtheta = d/dtheta <v, g(theta)> = d/dtheta (JVP of d along v).  The
 tangent network has the same linear structure as the linearised primal, so for layer l
@@ -27,8 +28,6 @@ from __future__ import annotations
 import ctypes as C
 
 import torch
-import torch.nn.functional as F
-from torch.func import functional_call, jvp
 
 from . import _lib
 
@@ -44,15 +43,6 @@ CHUNK = 65536      # poses per export chunk (bounds the dump buffers at ~1.4 GB 
 def _rows(dump, r0, n, B):
     """dump (T, 5504, 32) -> (B, n) matrix of rows [r0, r0+n)"""
     return dump[:, r0:r0 + n, :].permute(0, 2, 1).reshape(-1, n)[:B]
-
-
-def _pack_tangent(zdot, z0_rows):
-    """(B, w) tangent of the DFNet input -> [tile][128][32] floats"""
-    B, w = zdot.shape
-    T = (B + 31) // 32
-    buf = torch.zeros(T * 32, 128, device=zdot.device, dtype=torch.float32)
-    buf[:B, :w] = zdot
-    return buf.reshape(T, 32, 128).permute(0, 2, 1).contiguous()
 
 
 class _Exports:
@@ -79,16 +69,6 @@ class _Exports:
         return _rows(self.dump, G0_ROW, in_dim, self.B)
 
 
-def _tangent_exports(eng, x, normalise, zdot0):
-    B = x.shape[0]
-    T = (B + 31) // 32
-    dump = torch.empty(T, DUMP_ROWS, 32, device=x.device, dtype=torch.float32)
-    tan = _pack_tangent(zdot0, 128)
-    _lib.check(eng.lib.pndf_forward_tangent_export(eng._h, x.data_ptr(), B, int(normalise), tan.data_ptr(), dump.data_ptr(),
-                                                   torch.cuda.current_stream(x.device).cuda_stream))
-    return dump
-
-
 def _out_act_deriv(d, act, beta):
     """phi_out'(s) and phi_out''(s) recovered from d = phi_out(s): relu (relu / lrelu configs) or softplus(beta)."""
     if act == "softplus":
@@ -107,16 +87,36 @@ def _hidden_act_deriv(z_next, act, beta):
     return torch.where(z_next > 0, torch.ones_like(z_next), torch.full_like(z_next, slope)), None
 
 
-def _encoder_fn(net, normalise):
-    names = [n for n, _ in net.enc.named_parameters()] if net.enc is not None else []
-    params = {n: p for n, p in net.enc.named_parameters()} if net.enc is not None else {}
+ENC_FLOATS = 3516
 
-    def f(x, ps):
-        q = F.normalize(x, dim=1) if normalise else x
-        if net.enc is None:
-            return q.reshape(len(q), -1)
-        return functional_call(net.enc, ps, (q,))
-    return f, names, params
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _encoder_tangent(eng, x, v, normalise):
+    """tangent of the DFNet input along the pose tangent v, already in the [tile][128][32] layout of launch 2"""
+    B = x.shape[0]
+    tiles = torch.zeros((B + 31) // 32, 128, 32, device=x.device, dtype=torch.float32)
+    _lib.check(eng.lib.pndf_encoder_tangent(eng._h, x.data_ptr(), v.data_ptr(), B, int(normalise), tiles.data_ptr(), _stream(x)))
+    return tiles
+
+
+def _encoder_param_grads(eng, x, v, normalise, up1, upt, upz):
+    """(2, 3516) encoder parameter gradients: row 0 first-order objective, row 1 Eikonal objective"""
+    out = torch.empty(2, ENC_FLOATS, device=x.device, dtype=torch.float32)
+    ptr = lambda t: None if t is None else t.data_ptr()
+    _lib.check(eng.lib.pndf_encoder_param_grads(eng._h, x.data_ptr(), ptr(v), x.shape[0], int(normalise), ptr(up1), ptr(upt),
+                                                ptr(upz), out.data_ptr(), _stream(x)))
+    return out
+
+
+def _scatter_encoder_grads(net, flat, acc):
+    off = 0
+    for n, p in net.enc.named_parameters():
+        k = p.numel()
+        _accumulate(acc, "enc." + n, flat[off:off + k].reshape(p.shape))
+        off += k
 
 
 def _accumulate(acc, name, val):
@@ -138,7 +138,6 @@ def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_no
         g1, ge = {}, ({} if eik_weight is not None else None)
         dists, eik_sum = [], x.new_zeros(())
         Btot = x.shape[0]
-        enc_f, enc_names, enc_params = _encoder_fn(net, normalise)
         for c0 in range(0, Btot, CHUNK):
             xc = x[c0:c0 + CHUNK].contiguous()
             ex = _Exports(eng, xc, normalise)
@@ -154,29 +153,26 @@ def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_no
                 _accumulate(g1, f"dfnet.lin{l}.bias", da.sum(0))
             _accumulate(g1, "dfnet.lin6.weight", ((dl * gs) * Z[6]).sum(0, keepdim=True))
             _accumulate(g1, "dfnet.lin6.bias", (dl * gs).sum(0))
-            up0 = dl * ex.g0(in_dim)                                         # upstream on the encoder output
+            g0 = ex.g0(in_dim).contiguous()                                  # adjoint of the encoder output (unit upstream)
+            up0 = (dl * g0).contiguous()
             if eik_weight is None:
                 if net.enc is not None:
-                    with torch.enable_grad():
-                        z0 = enc_f(xc, enc_params)
-                        gps = torch.autograd.grad(z0, list(enc_params.values()), up0)
-                    for n, gp in zip(enc_names, gps):
-                        _accumulate(g1, "enc." + n, gp)
+                    _scatter_encoder_grads(net, _encoder_param_grads(eng, xc, None, normalise, up0, None, None)[0], g1)
                 continue
             # ---- Eikonal term
             g = ex.grad
             nrm = g.norm(2, dim=-1, keepdim=True)
             count = float((loss_norm if loss_norm is not None else Btot) * 21)
             eik_sum = eik_sum + ((nrm - 1) ** 2).sum()
-            v = (2.0 * (nrm - 1) / count) * (g / nrm)                        # dE/dg  (mean over all (b,j))
-            with torch.enable_grad():
-                z0_e, zdot0 = jvp(lambda xx: enc_f(xx, enc_params), (xc,), (v,))
-            dump_t = _tangent_exports(eng, xc, normalise, zdot0.detach())
-            Zd = [zdot0.detach()] + [_rows(dump_t, Z_ROWS[l][0], Z_ROWS[l][1], ex.B) for l in range(1, 7)]
+            v = ((2.0 * (nrm - 1) / count) * (g / nrm)).contiguous()         # dE/dg  (mean over all (b,j))
+            tan = _encoder_tangent(eng, xc, v, normalise)
+            dump_t = torch.empty(tan.shape[0], DUMP_ROWS, 32, device=xc.device, dtype=torch.float32)
+            _lib.check(eng.lib.pndf_forward_tangent_export(eng._h, xc.data_ptr(), ex.B, int(normalise), tan.data_ptr(),
+                                                           dump_t.data_ptr(), _stream(xc)))
+            Zd = [_rows(dump_t, 0, in_dim, ex.B)] + [_rows(dump_t, Z_ROWS[l][0], Z_ROWS[l][1], ex.B) for l in range(1, 7)]
             for l in range(6):
                 _accumulate(ge, f"dfnet.lin{l}.weight", A[l].t() @ Zd[l])
             _accumulate(ge, "dfnet.lin6.weight", (gs * Zd[6]).sum(0, keepdim=True))
-            up_z0dot = ex.g0(in_dim)                                         # dE/d(zdot_0) = adjoint of z_0 (unit upstream)
             up_z0 = None
             if act == "softplus":
                 # second-order adjoint chain (phi'' != 0): seven GEMMs on the exported tensors
@@ -192,21 +188,11 @@ def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_no
                     _accumulate(ge, f"dfnet.lin{l}.weight", pbar.t() @ Z[l])
                     _accumulate(ge, f"dfnet.lin{l}.bias", pbar.sum(0))
                     zbar = pbar @ W[l]
-                up_z0 = zbar
+                up_z0 = zbar.contiguous()
             if net.enc is not None:
-                # two reverse sweeps over ONE (jvp-augmented) encoder graph: first-order term and Eikonal term
-                with torch.enable_grad():
-                    obj1 = (z0_e * up0).sum()
-                    obj2 = (zdot0 * up_z0dot).sum()
-                    if up_z0 is not None:
-                        obj2 = obj2 + (z0_e * up_z0).sum()
-                    plist = list(enc_params.values())
-                    gp1 = torch.autograd.grad(obj1, plist, retain_graph=True)
-                    gp2 = torch.autograd.grad(obj2, plist, allow_unused=True)
-                for n, a1, a2 in zip(enc_names, gp1, gp2):
-                    _accumulate(g1, "enc." + n, a1)
-                    if a2 is not None:
-                        _accumulate(ge, "enc." + n, a2)
+                eg = _encoder_param_grads(eng, xc, v, normalise, up0, g0, up_z0)
+                _scatter_encoder_grads(net, eg[0], g1)
+                _scatter_encoder_grads(net, eg[1], ge)
         dist = torch.cat(dists, 0)
         eik = None
         if eik_weight is not None:
