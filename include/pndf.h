@@ -115,11 +115,12 @@ int pndf_forward_grad_debug(pndf_handle* h, const float* pose_dev, int64_t B, in
 
 /* Training support (model/posendf.py:78-99, model/train_posendf.py:93-99; host side in posendf_b200/train.py).
  * pndf_forward_grad_export = pndf_forward_grad (unit upstream gradient) that additionally writes, for EVERY 32-pose
- * tile t, all layer inputs z_l and all pre-activation adjoints to dump_dev[t][5504][32] (row map in DESIGN.md): the
- * operands of the weight-gradient GEMMs dW_l = sum_b adj_l[b] (x) z_l[b].
+ * pose b (padded to a multiple of 32), all layer inputs z_l and all pre-activation adjoints to dump_dev[b][5504]
+ * (column map in DESIGN.md): plain strided (B x width) operands of the weight-gradient GEMMs
+ * dW_l = sum_b adj_l[b] (x) z_l[b].
  * pndf_forward_tangent_export recomputes the forward pass and then pushes the tangent tan_dev[t][128][32] of the DFNet
- * input through the linearised network (forward mode), exporting the tangents of all layer inputs to rows [0,2752)
- * of dump_dev[t]: the second operand of the Eikonal term's weight gradients. */
+ * input through the linearised network (forward mode), exporting the tangents of all layer inputs to columns
+ * [0,2752) of dump_dev[b]: the second operand of the Eikonal term's weight gradients. */
 int pndf_forward_grad_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, float* dist_dev, float* grad_dev,
                              float* dump_dev, void* stream);
 int pndf_forward_tangent_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, const float* tan_dev,

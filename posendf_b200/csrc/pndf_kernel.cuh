@@ -529,11 +529,15 @@ __device__ __forceinline__ void splitk_combine(float (&acc)[8][TN], float* out, 
     }
 }
 
+// Export a [feature][pose] tile as rows of the pose-major dump: dump[pose][kDumpRows] (so that the host sees plain
+// strided (B x width) matrices, no repacking before the weight-gradient GEMMs).  `rows` is a multiple of 32 here, a warp
+// writes 32 consecutive features of one pose (coalesced); the transposed shared-memory read is 4-way bank conflicted,
+// which does not matter next to the GEMMs.
 __device__ __forceinline__ void dump_rows(float* dbg, int row0, const float* buf, int rows, int tid) {
     if (dbg == nullptr) return;
     for (int idx = tid; idx < rows * 32; idx += kGemmThreads) {
-        const int r = idx >> 5, m = idx & 31;
-        dbg[(size_t)(row0 + r) * 32 + m] = buf[swz(r, m)];
+        const int m = idx / rows, r = idx - m * rows;
+        dbg[(size_t)m * kDumpRows + row0 + r] = buf[swz(r, m)];
     }
 }
 

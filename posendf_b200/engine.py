@@ -124,7 +124,7 @@ class Engine:
         B = min(x.shape[0], 32)
         n = C.c_size_t()
         _lib.check(self.lib.pndf_debug_dump_floats(C.byref(n)))
-        dump = torch.zeros(n.value // 32, 32, device=self.device, dtype=torch.float32)
+        dump = torch.zeros(32, n.value // 32, device=self.device, dtype=torch.float32)     # pose-major: [pose][5504]
         dist = torch.empty(B, 1, device=self.device, dtype=torch.float32)
         grad = torch.empty(B, 21, 4, device=self.device, dtype=torch.float32)
         _lib.check(self.lib.pndf_forward_grad_debug(self._h, x.data_ptr(), B, int(normalise), dist.data_ptr(), grad.data_ptr(),

@@ -20,8 +20,8 @@ train=True (model/posendf.py:78-99: dist + manifold + Eikonal losses and their p
 Eikonal double backward) has a fused path too: posendf_b200/train.py (three fused launches exporting the operands of
 the weight-gradient GEMMs, cuBLAS for those batch reductions, torch autograd only for the 3 516-parameter encoder),
 selected with opt['train']['fused_train'] = True and checked against the reference's autograd to ~1e-6.  The default
-is plain torch autograd over the same submodules, because it is still faster (29 ms vs 43 ms per 32 768+32 768-sample
-step on B200: the fused path is CPU-bound in the encoder's ~2 000 tiny autograd ops).
+is plain torch autograd over the same submodules, because it is still slightly faster (29 / 32 ms vs 30 / 40 ms per
+32 768+32 768-sample step on B200 for lrelu / softplus).
 """
 from __future__ import annotations
 

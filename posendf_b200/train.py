@@ -41,8 +41,8 @@ CHUNK = 65536      # poses per export chunk (bounds the dump buffers at ~1.4 GB 
 
 
 def _rows(dump, r0, n, B):
-    """dump (T, 5504, 32) -> (B, n) matrix of rows [r0, r0+n)"""
-    return dump[:, r0:r0 + n, :].permute(0, 2, 1).reshape(-1, n)[:B]
+    """dump (Bpad, 5504) pose-major -> strided (B, n) view of columns [r0, r0+n) (no copy; cuBLAS takes the stride)"""
+    return dump[:B, r0:r0 + n]
 
 
 class _Exports:
@@ -50,7 +50,7 @@ class _Exports:
         B = x.shape[0]
         T = (B + 31) // 32
         self.B = B
-        self.dump = torch.empty(T, DUMP_ROWS, 32, device=x.device, dtype=torch.float32)
+        self.dump = torch.empty(T * 32, DUMP_ROWS, device=x.device, dtype=torch.float32)
         self.dist = torch.empty(B, 1, device=x.device, dtype=torch.float32)
         self.grad = torch.empty(B, 21, 4, device=x.device, dtype=torch.float32)
         _lib.check(eng.lib.pndf_forward_grad_export(eng._h, x.data_ptr(), B, int(normalise), self.dist.data_ptr(),
@@ -111,23 +111,34 @@ def _encoder_param_grads(eng, x, v, normalise, up1, upt, upz):
     return out
 
 
-def _scatter_encoder_grads(net, flat, acc):
-    off = 0
-    for n, p in net.enc.named_parameters():
-        k = p.numel()
-        _accumulate(acc, "enc." + n, flat[off:off + k].reshape(p.shape))
-        off += k
+class _FlatGrads:
+    """one flat fp32 gradient vector in the reference's parameter order with per-parameter views; GEMM results are
+    accumulated straight into the views, the encoder kernel's 3 516 floats into the leading slice."""
 
+    def __init__(self, net):
+        ps = list(net.named_parameters())
+        self.flat = torch.zeros(sum(p.numel() for _, p in ps), device=ps[0][1].device, dtype=torch.float32)
+        self.views, off = {}, 0
+        for n, p in ps:
+            self.views[n] = self.flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
 
-def _accumulate(acc, name, val):
-    acc[name] = val if name not in acc else acc[name] + val
+    def addmm(self, name, a_t, b):          # view += a_t @ b
+        self.views[name].addmm_(a_t, b)
+
+    def add(self, name, val):
+        v = self.views[name]
+        v.add_(val.reshape(v.shape))
+
+    def add_encoder(self, flat3516):
+        self.flat[:ENC_FLOATS].add_(flat3516)
 
 
 def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_norm=None):
     """Parameter gradients of  sum_b delta[b] * d(x[b])  (+ those of the Eikonal term if eik_weight is not None), the
     distances and the Eikonal value.  x (B,21,4) fp32 CUDA; delta_fn(dist_chunk, lo, hi) -> (hi-lo,) upstream gradient
     on d for poses [lo,hi) (evaluated after the distances are known, so no extra forward launch is needed).  Returns
-    (grads_first: dict name->tensor, grads_eik: dict or None, dist (B,1), eikonal scalar or None)."""
+    (first-order _FlatGrads, Eikonal _FlatGrads or None, dist (B,1), eikonal scalar or None)."""
     eng = net.engine()
     cfg = net._cfg
     in_dim, act, beta = cfg["in_dim"], cfg["df_act"], cfg["df_beta"]
@@ -135,7 +146,7 @@ def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_no
     old_tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
-        g1, ge = {}, ({} if eik_weight is not None else None)
+        g1, ge = _FlatGrads(net), (_FlatGrads(net) if eik_weight is not None else None)
         dists, eik_sum = [], x.new_zeros(())
         Btot = x.shape[0]
         for c0 in range(0, Btot, CHUNK):
@@ -149,15 +160,15 @@ def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_no
             # ---- first-order term: dW_l = (delta * a_l)^T z_l
             for l in range(6):
                 da = dl * A[l]
-                _accumulate(g1, f"dfnet.lin{l}.weight", da.t() @ Z[l])
-                _accumulate(g1, f"dfnet.lin{l}.bias", da.sum(0))
-            _accumulate(g1, "dfnet.lin6.weight", ((dl * gs) * Z[6]).sum(0, keepdim=True))
-            _accumulate(g1, "dfnet.lin6.bias", (dl * gs).sum(0))
+                g1.addmm(f"dfnet.lin{l}.weight", da.t(), Z[l])
+                g1.add(f"dfnet.lin{l}.bias", da.sum(0))
+            g1.add("dfnet.lin6.weight", ((dl * gs) * Z[6]).sum(0))
+            g1.add("dfnet.lin6.bias", (dl * gs).sum(0))
             g0 = ex.g0(in_dim).contiguous()                                  # adjoint of the encoder output (unit upstream)
-            up0 = (dl * g0).contiguous()
+            up0 = dl * g0
             if eik_weight is None:
                 if net.enc is not None:
-                    _scatter_encoder_grads(net, _encoder_param_grads(eng, xc, None, normalise, up0, None, None)[0], g1)
+                    g1.add_encoder(_encoder_param_grads(eng, xc, None, normalise, up0, None, None)[0])
                 continue
             # ---- Eikonal term
             g = ex.grad
@@ -166,34 +177,34 @@ def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_no
             eik_sum = eik_sum + ((nrm - 1) ** 2).sum()
             v = ((2.0 * (nrm - 1) / count) * (g / nrm)).contiguous()         # dE/dg  (mean over all (b,j))
             tan = _encoder_tangent(eng, xc, v, normalise)
-            dump_t = torch.empty(tan.shape[0], DUMP_ROWS, 32, device=xc.device, dtype=torch.float32)
+            dump_t = torch.empty(tan.shape[0] * 32, DUMP_ROWS, device=xc.device, dtype=torch.float32)
             _lib.check(eng.lib.pndf_forward_tangent_export(eng._h, xc.data_ptr(), ex.B, int(normalise), tan.data_ptr(),
                                                            dump_t.data_ptr(), _stream(xc)))
             Zd = [_rows(dump_t, 0, in_dim, ex.B)] + [_rows(dump_t, Z_ROWS[l][0], Z_ROWS[l][1], ex.B) for l in range(1, 7)]
             for l in range(6):
-                _accumulate(ge, f"dfnet.lin{l}.weight", A[l].t() @ Zd[l])
-            _accumulate(ge, "dfnet.lin6.weight", (gs * Zd[6]).sum(0, keepdim=True))
+                ge.addmm(f"dfnet.lin{l}.weight", A[l].t(), Zd[l])
+            ge.add("dfnet.lin6.weight", (gs * Zd[6]).sum(0))
             up_z0 = None
             if act == "softplus":
                 # second-order adjoint chain (phi'' != 0): seven GEMMs on the exported tensors
                 sdot = Zd[6] @ W[6].t()                                      # (B,1)
                 pbar = gss * sdot                                            # adjoint of s
-                _accumulate(ge, "dfnet.lin6.weight", (pbar * Z[6]).sum(0, keepdim=True))
-                _accumulate(ge, "dfnet.lin6.bias", pbar.sum(0))
+                ge.add("dfnet.lin6.weight", (pbar * Z[6]).sum(0))
+                ge.add("dfnet.lin6.bias", pbar.sum(0))
                 zbar = pbar @ W[6]                                           # (B,64) adjoint of z_6
                 for l in range(5, -1, -1):
                     d1, ratio = _hidden_act_deriv(Z[l + 1], act, beta)       # phi'(pre_l), phi''/phi'
                     pdot = Zd[l + 1] / d1.clamp_min(1e-30)                   # tangent of pre_l
                     pbar = zbar * d1 + A[l] * ratio * pdot                   # A[l] = gbar_{l+1} * phi'
-                    _accumulate(ge, f"dfnet.lin{l}.weight", pbar.t() @ Z[l])
-                    _accumulate(ge, f"dfnet.lin{l}.bias", pbar.sum(0))
+                    ge.addmm(f"dfnet.lin{l}.weight", pbar.t(), Z[l])
+                    ge.add(f"dfnet.lin{l}.bias", pbar.sum(0))
                     zbar = pbar @ W[l]
                 up_z0 = zbar.contiguous()
             if net.enc is not None:
                 eg = _encoder_param_grads(eng, xc, v, normalise, up0, g0, up_z0)
-                _scatter_encoder_grads(net, eg[0], g1)
-                _scatter_encoder_grads(net, eg[1], ge)
-        dist = torch.cat(dists, 0)
+                g1.add_encoder(eg[0])
+                ge.add_encoder(eg[1])
+        dist = torch.cat(dists, 0) if len(dists) > 1 else dists[0]
         eik = None
         if eik_weight is not None:
             eik = eik_sum / float((loss_norm if loss_norm is not None else Btot) * 21)
@@ -204,11 +215,10 @@ def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_no
 
 class FusedTrainLosses(torch.autograd.Function):
     """(dist loss, manifold loss, Eikonal loss) of model/posendf.py:85-96 with parameter gradients from the fused path.
-    backward() combines the three per-term gradient sets with the upstream weights (model/train_posendf.py:95-98)."""
+    backward() combines the three per-term gradient vectors with the upstream weights (model/train_posendf.py:95-98)."""
 
     @staticmethod
     def forward(ctx, net, pose, dist_gt, man_poses, loss_type, want_eik, *params):
-        names = [n for n, _ in net.named_parameters()]
         B = pose.shape[0]
 
         def delta_dist(dist, lo, hi):
@@ -218,12 +228,12 @@ class FusedTrainLosses(torch.autograd.Function):
         g_dist, g_eik, d, eik = fused_param_grads(net, pose, delta_dist, True, 1.0 if want_eik else None)
         diff = d[:, 0] - dist_gt
         loss_d = diff.abs().mean() if loss_type == "l1" else (diff * diff).mean()
-        g_man, loss_m = {}, loss_d.new_zeros(())
+        g_man, loss_m = None, loss_d.new_zeros(())
         if want_eik:     # the reference only reports / trains the manifold term together with the Eikonal term (posendf.py:94-99)
             Bm = man_poses.shape[0]
             g_man, _, dm, _ = fused_param_grads(net, man_poses, lambda dist, lo, hi: torch.sign(dist[:, 0]) / Bm, False, None)
             loss_m = dm.abs().mean()
-        ctx.grads = [[gd.get(n) for n in names] for gd in (g_dist, g_man, g_eik if g_eik is not None else {})]
+        ctx.flats = [g.flat if g is not None else None for g in (g_dist, g_man, g_eik)]
         ctx.shapes = [p.shape for p in params]
         if not want_eik:
             eik = loss_d.new_zeros(())
@@ -231,16 +241,16 @@ class FusedTrainLosses(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gd, gm, ge):
-        out = []
-        for i, shp in enumerate(ctx.shapes):
-            tot = None
-            for up, gset in zip((gd, gm, ge), ctx.grads):
-                gi = gset[i]
-                if gi is None or up is None:
-                    continue
-                term = up * gi.reshape(shp)
-                tot = term if tot is None else tot + term
-            out.append(tot)
+        tot = None
+        for up, flat in zip((gd, gm, ge), ctx.flats):
+            if flat is None or up is None:
+                continue
+            tot = up * flat if tot is None else tot.add_(up * flat)
+        out, off = [], 0
+        for shp in ctx.shapes:
+            n = shp.numel()
+            out.append(tot[off:off + n].view(shp))
+            off += n
         return (None, None, None, None, None, None, *out)
 
 

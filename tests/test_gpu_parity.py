@@ -59,7 +59,7 @@ def test_every_layer_tile_matches_oracle(name):
     eng = make_engine(meta, params)
     dist, grad, dump = eng.forward_grad_debug(torch.from_numpy(poses).cuda())
     torch.cuda.synchronize()
-    dump = dump.cpu().numpy()
+    dump = dump.cpu().numpy().T          # pose-major export -> [row][pose]
     os.makedirs(OUT, exist_ok=True)
     lines = []
     worst = 0.0
