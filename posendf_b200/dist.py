@@ -55,3 +55,20 @@ def project_sharded(net, poses: torch.Tensor, steps: int = 10, renorm: bool = Fa
     lo, hi = shard_bounds(n, world, rank)
     x, d = net.project(poses.reshape(-1, 21, 4)[lo:hi], steps=steps, renorm=renorm)
     return all_gather_ragged(x, n, group), all_gather_ragged(d, n, group)
+
+
+def allreduce_gradients(net, group=None):
+    """Data-parallel training (config 5): average the parameter gradients of all ranks after backward() with ONE
+    all-reduce of the flattened 1 365 565 fp32 values (5.46 MB; losses are means over equal shards, so averaging the
+    per-rank gradients reproduces the single-process step)."""
+    params = [p for p in net.parameters() if p.grad is not None]
+    if not params:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(dist.get_world_size(group))
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n

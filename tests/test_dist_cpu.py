@@ -47,3 +47,27 @@ def _worker(rank, world, port, n):
 @pytest.mark.parametrize("n", [64, 1000, 33])
 def test_all_gather_ragged_world2_gloo(n):
     mp.spawn(_worker, args=(2, _free_port(), n), nprocs=2, join=True)
+
+
+def _grad_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from posendf_b200.dist import allreduce_gradients
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 1))
+        x = torch.arange(40, dtype=torch.float32).reshape(8, 5) / 40.0
+        lo, hi = rank * 4, rank * 4 + 4
+        net(x[lo:hi]).abs().mean().backward()                 # per-rank mean over an equal shard
+        allreduce_gradients(net)
+        ref = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 1))
+        ref.load_state_dict(net.state_dict())
+        ref(x).abs().mean().backward()                        # single-process step over the full batch
+        for p, q in zip(net.parameters(), ref.parameters()):
+            assert torch.allclose(p.grad, q.grad, atol=1e-7)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_equals_single_process_step_world2_gloo():
+    mp.spawn(_grad_worker, args=(2, _free_port()), nprocs=2, join=True)
