@@ -8,16 +8,16 @@
 //   (net_modules.py:46-72) -> analytic reverse pass (replaces torch.autograd.grad, model/posendf.py:18-27)
 //   -> normalise Jacobian -> x <- x - d * dd/dx (experiments/sample_poses.py:74), optionally K times.
 //
-// The DFNet layers (99.8 % of the flops) run as register-tiled fp32 FFMA GEMMs: 256 compute threads, each
-// owning an 8-pose x TN-feature micro-tile; activations live in shared memory as [feature][pose] with a
-// 16-byte XOR swizzle; weights are streamed from L2 through a 4-stage ring of 16 KB slabs filled by a
-// rotating elected lane with cp.async.bulk (TMA 1-D bulk copies) + mbarriers.  The host pre-packs all
-// weights into ONE linear "slab stream" in exactly the order the tile consumes them (forward layout
-// W^T[k][n] for the forward ops, native W[out][in] for the reverse ops), so the producer just walks
-// memory.  The 1024-wide layer never exists in full: L2's output is produced in two 512-feature chunks
-// that are consumed immediately as K-chunks of L3 (accumulators stay in registers); the reverse pass
-// mirrors this.  Activation derivatives are 1 bit per unit in shared memory for relu / lrelu and fp32
-// in an L2-resident per-CTA scratch for softplus.
+// The DFNet layers (99.8 % of the flops) run as register-tiled fp32 GEMMs on the packed FFMA2 pipe: 256 threads,
+// each owning an 8-pose x 8-feature micro-tile; activations live in shared memory as [feature][pose] with a 16-byte
+// XOR swizzle; every warp streams ONLY the 64 feature columns it multiplies through its own private 2-stage ring of
+// 4 KB slabs (cp.async.bulk / TMA 1-D copies completing on per-warp mbarriers, refilled by the warp itself).  The
+// host pre-packs all weights into eight interleaved per-warp streams in exactly the order a tile consumes them
+// (forward layout W^T[k][n] for the forward ops, native W[out][in] for the reverse ops).  The 1024-wide layer never
+// exists in full: L2's output is produced in two 512-feature chunks that are consumed immediately as K-chunks of L3
+// (accumulators stay in registers); the reverse pass mirrors this; the 256-wide ops run split-K.  Activation
+// derivatives are 1 bit per unit in shared memory for relu / lrelu and fp32 in an L2-resident per-CTA scratch for
+// softplus.  MODE 2 replays the forward ops as a forward-mode tangent pass (training, Eikonal term).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,7 +25,7 @@
 namespace pndf {
 
 constexpr int kTileM = 32;            // poses per CTA tile
-constexpr int kGemmThreads = 256;     // 8 compute warps; the weight-slab producer role rotates among them
+constexpr int kGemmThreads = 256;     // 8 warps, all of them compute (there is no producer warp)
 constexpr int kThreads = 256;         // (256 threads -> 255 registers/thread for the 2x64 fused accumulators)
 // Weight streaming: every warp owns a PRIVATE 2-stage ring of 4 KB slabs holding only the 64 (16, 8) feature columns
 // that warp multiplies -- R = 1024 / columns rows per slab.  The warp that consumed a slab refills it itself
@@ -98,37 +98,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded spin: a mismatch between the producer's and the consumers' slab counts must end in a trap
-// (launch error), never in a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) __trap();
-    }
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 __device__ __forceinline__ void gemm_bar() { __syncthreads(); }
 
