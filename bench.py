@@ -271,7 +271,7 @@ def main():
     if rank == 0:
         peaks, peak_src = measured_peaks()
         p_ffma = fp32_peak_tflops(local_rank, 0)
-        p_ffma2 = fp32_peak_tflops(local_rank, 1)
+        p_ffma2 = max(fp32_peak_tflops(local_rank, 1), fp32_peak_tflops(local_rank, 5))   # two operand orders, best one
         p_fp32 = max(p_ffma, p_ffma2)
         rate = world * B * args.steps / (total_ms * 1e-3)
         k_rate = B / (kernel_ms * 1e-3)

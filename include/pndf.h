@@ -141,7 +141,8 @@ int pndf_encoder_param_grads(pndf_handle* h, const float* pose_dev, const float*
 
 /* Measurement helpers used by bench.py (not on the data path):
  *   pndf_fp32_peak: in-process FFMA micro-benchmark, dense fp32 FMA TFLOP/s of this GPU right now.
- *     variant 0 = scalar FFMA, 1 = packed FFMA2 (fma.rn.f32x2).
+ *     variant 0 = scalar FFMA, 1 / 5 = packed FFMA2 (fma.rn.f32x2) with the pose scalar / the feature pair as the
+ *     reused operand, 2-4 / 10-11 = probes used while tuning (operand traffic, legacy mma.sync).
  *   pndf_launch_count: number of kernel launches this handle has enqueued so far. */
 int pndf_fp32_peak(int device, int variant, double* tflops);
 int pndf_launch_count(pndf_handle* h, int64_t* n);

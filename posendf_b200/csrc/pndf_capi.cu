@@ -508,6 +508,21 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            } else if (VARIANT == 5) {
+                // same FMAs, feature pair outermost (the b pair is the reused operand, 8 pose scalars stream past it)
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    unsigned long long bb;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b[j]), "f"(b[j + 1]));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        unsigned long long aa, cc;
+                        asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a[i]));
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(cc) : "f"(acc[i][j]), "f"(acc[i][j + 1]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cc) : "l"(aa), "l"(bb));
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[i][j]), "=f"(acc[i][j + 1]) : "l"(cc));
+                    }
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -602,6 +617,7 @@ extern "C" int pndf_fp32_peak(int device, int variant, double* tflops) {
         else if (variant == 2) fp32_peak_kernel<2><<<blocks, threads>>>(out, iters, 0.5f);
         else if (variant == 3) fp32_peak_kernel<3><<<blocks, threads>>>(out, iters, 0.5f);
         else if (variant == 4) fp32_peak_kernel<4><<<blocks, threads>>>(out, iters, 0.5f);
+        else if (variant == 5) fp32_peak_kernel<5><<<blocks, threads>>>(out, iters, 0.5f);
         else if (variant == 10) mma_peak_kernel<10><<<blocks, threads>>>(out, iters, 0.5f);
         else mma_peak_kernel<11><<<blocks, threads>>>(out, iters, 0.5f);
         CUDA_OK(cudaEventRecord(e1));
