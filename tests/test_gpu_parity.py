@@ -296,3 +296,46 @@ def test_denoise_prior_loop_vs_oracle():
     err = np.abs(x - xref)
     assert np.abs(xref - aa).max() > 0.05
     assert np.median(err) < 2e-6 and (err > 1e-4).mean() < 0.01, (np.median(err), err.max(), (err > 1e-4).mean())
+
+
+def test_two_handles_and_side_stream_do_not_interfere():
+    """two engines with different weights / activations alive at once, one driven from a non-default stream"""
+    from posendf_b200.engine import Engine
+    pa, pb = synth.make_params(1), synth.make_params(2)
+    ea = Engine(device=0, enc_act="lrelu", df_act="lrelu")
+    eb = Engine(device=0, enc_act="softplus", df_act="softplus")
+    ea.set_weights_flat(synth.flatten_params(pa)); eb.set_weights_flat(synth.flatten_params(pb))
+    poses = synth.make_poses(17, 300)
+    x = torch.from_numpy(poses).cuda()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        db, gb = eb.forward_grad(x)
+    da, ga = ea.forward_grad(x)
+    side.synchronize(); torch.cuda.synchronize()
+    p64 = lambda p: {k: v.astype(np.float64) for k, v in p.items()}
+    ra, _ = onp.forward_grad(p64(pa), poses.astype(np.float64), onp.default_cfg())
+    rb, _ = onp.forward_grad(p64(pb), poses.astype(np.float64), onp.default_cfg(enc_act="softplus", df_act="softplus"))
+    assert np.max(rel_err(da.cpu().numpy(), ra)) < 1e-5 and np.max(rel_err(db.cpu().numpy(), rb)) < 1e-5
+
+
+def test_api_misuse_fails_loudly():
+    from posendf_b200.engine import Engine
+    eng = Engine(device=0)
+    x = torch.zeros(4, 21, 4, device="cuda")
+    with pytest.raises(RuntimeError, match="pndf_set_weights"):
+        eng.forward(x)                                     # no weights yet
+    with pytest.raises(RuntimeError, match="wrong parameter count"):
+        eng.set_weights_flat(np.zeros(10, dtype=np.float32))
+    eng.set_weights_flat(synth.flatten_params(synth.make_params(1)))
+    with pytest.raises(RuntimeError):
+        eng.forward(torch.zeros(4, 21, 4))                 # CPU tensor
+    with pytest.raises(RuntimeError):
+        eng.project_(torch.zeros(8, 21, 4, device="cuda")[::2])   # non-contiguous in-place target
+    with pytest.raises(RuntimeError, match="steps"):
+        eng.project_(x.clone(), steps=0)
+    with pytest.raises(RuntimeError, match="amass.yaml"):
+        Engine(device=0, dims=(128, 128))
+    # fp64 / non-contiguous inputs of the out-of-place entry points are converted, not rejected
+    d = eng.forward(torch.zeros(8, 21, 4, device="cuda", dtype=torch.float64)[::2] + 0.1)
+    assert d.shape == (4, 1) and torch.isfinite(d).all()
