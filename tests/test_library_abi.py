@@ -50,3 +50,12 @@ def test_no_cpu_fallback_without_gpu():
     from posendf_b200.engine import Engine
     with pytest.raises(RuntimeError):
         Engine(device=0)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """no libpndf.so -> RuntimeError naming the build command, never a silent eager / CPU path"""
+    from posendf_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libpndf.so"))
+    with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
+        _lib.load()
