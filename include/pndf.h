@@ -139,6 +139,15 @@ int pndf_encoder_param_grads(pndf_handle* h, const float* pose_dev, const float*
                              const float* up_first_dev, const float* up_tangent_dev, const float* up_second_dev,
                              float* grads_dev, void* stream);
 
+/* Distance-label rerank of the dataset preparation (data/dist_utils.py:19-30 `euc`, :41-50 `geo`, topk at
+ * data/prepare_traindata.py:156): for each of Q query poses (Q*84 floats) the 5 nearest of its K candidates, given as
+ * int32 indices (Q*K) into a database of unit-quaternion poses (N*84 floats).  metric 0 = geo: mean_j (1 - |<q_j, q'_j>|),
+ * 1 = euc: mean_j |q_j - q'_j|; weighted != 0 uses the reference's normalised joint ranks instead of the mean.
+ * out_val_dev: Q*5 ascending distances, out_pos_dev: Q*5 positions inside the candidate list (torch.topk's indices).
+ * Stateless (no handle); HBM-bound: 336 B read per (query, candidate). */
+int pndf_knn_rerank(int device, const float* query_dev, int64_t Q, const float* database_dev, const int32_t* cand_dev, int K,
+                    int metric, int weighted, float* out_val_dev, int32_t* out_pos_dev, void* stream);
+
 /* Measurement helpers used by bench.py (not on the data path):
  *   pndf_fp32_peak: in-process FFMA micro-benchmark, dense fp32 FMA TFLOP/s of this GPU right now.
  *     variant 0 = scalar FFMA, 1 / 5 = packed FFMA2 (fma.rn.f32x2) with the pose scalar / the feature pair as the

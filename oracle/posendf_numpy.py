@@ -288,3 +288,27 @@ def denoise_prior(params, aa, cfg, iterations=10, steps_per_iter=50, lr=0.02, be
             denom = np.sqrt(v) / np.sqrt(1 - betas[1] ** t) + eps
             x = x - step * (m / denom)
     return x, d.reshape(S, T), np.array(hist)
+
+
+# ----------------------------------------------------------------------------- distance-label rerank
+JOINT_RANK = (7, 7, 7, 6, 6, 6, 5, 5, 5, 4, 4, 4, 4, 4, 3, 3, 3, 2, 2, 1, 1)     # data/dist_utils.py:15,37
+
+
+def knn_rerank(query, database, cand_idx, metric="geo", weighted=False, k=5):
+    """data/dist_utils.py:19-30 (euc) / :41-50 (geo) + torch.topk(k, largest=False): for every query pose the k
+    nearest of its candidate poses.  query (Q,21,4), database (N,21,4), cand_idx (Q,K) -> (values (Q,k) ascending,
+    positions inside the candidate list (Q,k))."""
+    q = np.asarray(query)
+    cand = np.asarray(database)[np.asarray(cand_idx)]                      # (Q,K,21,4)
+    w = np.asarray(JOINT_RANK, dtype=q.dtype)
+    w = w / np.maximum(np.sqrt(np.sum(w * w)), 1e-12)                      # F.normalize(joint_rank, dim=0)
+    if metric == "geo":
+        per_joint = 1 - np.abs(np.sum(cand * q[:, None], axis=3))          # (Q,K,21)
+    elif metric == "euc":
+        diff = q[:, None] - cand
+        per_joint = np.sqrt(np.sum(diff * diff, axis=3))
+    else:
+        raise ValueError(metric)
+    dis = np.sum(w * per_joint, axis=2) if weighted else np.mean(per_joint, axis=2)
+    order = np.argsort(dis, axis=1, kind="stable")[:, :k]
+    return np.take_along_axis(dis, order, axis=1), order

@@ -4,6 +4,7 @@
 #include "pndf_kernel.cuh"
 #include "pndf_denoise.cuh"
 #include "pndf_encoder_train.cuh"
+#include "pndf_knn.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -452,6 +453,21 @@ int pndf_encoder_param_grads(pndf_handle* h, const float* pose_dev, const float*
     enc_grad_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(p);
     CUDA_OK(cudaGetLastError());
     h->launches++;
+    return 0;
+}
+
+int pndf_knn_rerank(int device, const float* query_dev, int64_t Q, const float* database_dev, const int32_t* cand_dev, int K,
+                    int metric, int weighted, float* out_val_dev, int32_t* out_pos_dev, void* stream) {
+    if (Q == 0) return 0;
+    if (Q < 0 || K < kKnnK || !query_dev || !database_dev || !cand_dev || !out_val_dev || !out_pos_dev)
+        return fail("pndf_knn_rerank: null argument or K < 5");
+    if (metric != 0 && metric != 1) return fail("pndf_knn_rerank: metric must be 0 (geo) or 1 (euc)");
+    CUDA_OK(cudaSetDevice(device));
+    KnnParams p{};
+    p.query = query_dev; p.database = database_dev; p.cand = cand_dev; p.out_val = out_val_dev; p.out_pos = out_pos_dev;
+    p.Q = Q; p.K = K; p.metric = metric; p.weighted = weighted;
+    knn_rerank_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, (cudaStream_t)stream>>>(p);
+    CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -147,3 +147,20 @@ def fp32_peak_tflops(device=0, variant=0) -> float:
     v = C.c_double()
     _lib.check(lib.pndf_fp32_peak(int(device), int(variant), C.byref(v)))
     return v.value
+
+
+def knn_rerank(query, database, cand_idx, metric="geo", weighted=False):
+    """data/dist_utils.py `geo` / `euc` .dist_calc + topk(5): CUDA tensors query (Q,21,4) fp32, database (N,21,4) fp32,
+    cand_idx (Q,K) int32 -> (distances (Q,5) ascending, positions inside the candidate lists (Q,5) int32)."""
+    lib = _lib.load()
+    q = query.detach().to(torch.float32).reshape(-1, 84).contiguous()
+    db = database.detach().to(torch.float32).reshape(-1, 84).contiguous()
+    ci = cand_idx.detach().to(torch.int32).contiguous()
+    if not (q.is_cuda and db.is_cuda and ci.is_cuda):
+        raise RuntimeError("knn_rerank needs CUDA tensors (there is no CPU fallback)")
+    Q, K = ci.shape
+    val = torch.empty(Q, 5, device=q.device, dtype=torch.float32)
+    pos = torch.empty(Q, 5, device=q.device, dtype=torch.int32)
+    _lib.check(lib.pndf_knn_rerank(q.device.index or 0, q.data_ptr(), Q, db.data_ptr(), ci.data_ptr(), K,
+                                   {"geo": 0, "euc": 1}[metric], int(weighted), val.data_ptr(), pos.data_ptr(), _stream_ptr(q.device)))
+    return val, pos
