@@ -530,33 +530,26 @@ __device__ __forceinline__ float grp_get(float v, int src_l, const EncLane& e) {
 // first part shared by forward and reverse: u, the two hidden units of this lane, all 10 hidden values, and this
 // lane's output feature (o = min(l,5)).  d1a/d1b/d2 = activation derivatives at this lane's units.
 // qs = column-normalised pose tile [pose][85]; apar = slope (relu 0 / lrelu 0.01) or softplus beta.
-template <bool SOFT>
-__device__ __forceinline__ void bone_forward(const float* __restrict__ w, bool root, const float* qs, const float* feat, int i,
+// ROOT is a compile-time flag so that the body is branch-free and two independent joints can be interleaved.
+template <bool SOFT, bool ROOT>
+__device__ __forceinline__ void bone_forward(const float* __restrict__ w, const float* __restrict__ qs, const float* feat, int i,
                                              int par, const EncLane& e, float apar, float (&u)[10], float (&h)[10], float& f,
                                              float& d1a, float& d1b, float& d2) {
-    const int fin = root ? 4 : 10;
+    constexpr int fin = ROOT ? 4 : 10;
 #pragma unroll
     for (int cpt = 0; cpt < 4; ++cpt) u[cpt] = qs[e.m * kXS + i * 4 + cpt];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) u[4 + r] = root ? 0.0f : feat[swz(par * 6 + r, e.m)];
+    for (int r = 0; r < 6; ++r) u[4 + r] = ROOT ? 0.0f : feat[swz(par * 6 + r, e.m)];
     const int oa = e.l, ob = min(8 + e.l, 9);
     const float* w1 = w;
     const float* b1 = w + 10 * fin;
     const float* w2 = b1 + 10;
     const float* b2 = w2 + 60;
     float sa = b1[oa], sb = b1[ob];
-    if (root) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            sa = fmaf(w1[oa * 4 + k], u[k], sa);
-            sb = fmaf(w1[ob * 4 + k], u[k], sb);
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            sa = fmaf(w1[oa * 10 + k], u[k], sa);
-            sb = fmaf(w1[ob * 10 + k], u[k], sb);
-        }
+    for (int k = 0; k < fin; ++k) {
+        sa = fmaf(w1[oa * fin + k], u[k], sa);
+        sb = fmaf(w1[ob * fin + k], u[k], sb);
     }
     const float ha = act_t<SOFT>(sa, apar, d1a);
     const float hb = act_t<SOFT>(sb, apar, d1b);
@@ -571,73 +564,137 @@ __device__ __forceinline__ void bone_forward(const float* __restrict__ w, bool r
     f = act_t<SOFT>(s2, apar, d2);
 }
 
+// Joints are walked in a fixed schedule that pairs two joints of independent sub-trees per step (the legs / the arms),
+// so that their dependent FMA / shuffle chains interleave: 12 steps instead of 21.  Every joint appears after its parent.
+// (pairs: (1,0) (3,2) (5,4) (7,6) (9,8) (12,10) (14,11) (16,13) (17,15), then 18, 19, 20 alone.)
+template <bool SOFT, bool RA, bool RB>
+__device__ __forceinline__ void enc_fwd_pair(const float* encw, const float* qs, float* feat, float* stash, const EncLane& e,
+                                             float apar, int ia, int ib) {
+    float ua[10], ha[10], fa, xa, ya, za, ub[10], hb[10], fb, xb, yb, zb;
+    bone_forward<SOFT, RA>(encw + enc_off(ia), qs, feat, ia, c_parent[ia], e, apar, ua, ha, fa, xa, ya, za);
+    bone_forward<SOFT, RB>(encw + enc_off(ib), qs, feat, ib, c_parent[ib], e, apar, ub, hb, fb, xb, yb, zb);
+    if (e.l < 6) {
+        feat[swz(ia * 6 + e.l, e.m)] = fa;
+        feat[swz(ib * 6 + e.l, e.m)] = fb;
+        if (stash != nullptr) {
+            stash[(ia * 6 + e.l) * 32 + e.m] = fa;
+            stash[(ib * 6 + e.l) * 32 + e.m] = fb;
+        }
+    }
+    __syncwarp();
+}
+template <bool SOFT>
+__device__ __forceinline__ void enc_fwd_one(const float* encw, const float* qs, float* feat, float* stash, const EncLane& e,
+                                            float apar, int i) {
+    float u[10], h[10], f, x, y, z;
+    bone_forward<SOFT, false>(encw + enc_off(i), qs, feat, i, c_parent[i], e, apar, u, h, f, x, y, z);
+    if (e.l < 6) {
+        feat[swz(i * 6 + e.l, e.m)] = f;
+        if (stash != nullptr) stash[(i * 6 + e.l) * 32 + e.m] = f;
+    }
+    __syncwarp();
+}
+
 // forward encoder for this lane's pose; features are written as rows [i*6+o][m] of `feat` (and, if stash != nullptr,
 // to the CTA's L2-resident stash so that the reverse pass does not have to recompute them).
 template <bool SOFT>
 __device__ __forceinline__ void encoder_forward(const float* encw, const float* qs, float* feat, float* stash, const EncLane& e,
                                                 float apar) {
-    for (int i = 0; i < 21; ++i) {
-        const int par = c_parent[i];
-        float u[10], h[10], f, d1a, d1b, d2;
-        bone_forward<SOFT>(encw + enc_off(i), par < 0, qs, feat, i, par, e, apar, u, h, f, d1a, d1b, d2);
-        if (e.l < 6) {
-            feat[swz(i * 6 + e.l, e.m)] = f;
-            if (stash != nullptr) stash[(i * 6 + e.l) * 32 + e.m] = f;
-        }
-        __syncwarp();
-    }
+    enc_fwd_pair<SOFT, true, true>(encw, qs, feat, stash, e, apar, 1, 0);
+    enc_fwd_pair<SOFT, false, true>(encw, qs, feat, stash, e, apar, 3, 2);
+    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 5, 4);
+    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 7, 6);
+    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 9, 8);
+    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 12, 10);
+    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 14, 11);
+    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 16, 13);
+    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 17, 15);
+    enc_fwd_one<SOFT>(encw, qs, feat, stash, e, apar, 18);
+    enc_fwd_one<SOFT>(encw, qs, feat, stash, e, apar, 19);
+    enc_fwd_one<SOFT>(encw, qs, feat, stash, e, apar, 20);
 }
 
-// reverse encoder: features in `feat`, feature gradients in rows [0,126) of `gbuf` (accumulated in place, reverse
-// joint order is a reverse topological order), quaternion gradients -> rows [128+e] of `gbuf`.
+// reverse step of one joint: everything up to (not including) the writes.  ua/ub = this lane's gradient w.r.t. its input
+// elements j = l (and 8+l for l < 2, non-root joints).
+template <bool SOFT, bool ROOT>
+__device__ __forceinline__ void bone_backward(const float* encw, const float* qs, const float* feat, const float* gbuf, int i,
+                                              const EncLane& e, float apar, float& ua, float& ub) {
+    constexpr int fin = ROOT ? 4 : 10;
+    const int par = c_parent[i];
+    const float* w = encw + enc_off(i);
+    float u[10], h[10], f, d1a, d1b, d2;
+    bone_forward<SOFT, ROOT>(w, qs, feat, i, par, e, apar, u, h, f, d1a, d1b, d2);
+    const float* w1 = w;
+    const float* w2 = w + 10 * fin + 10;
+    // t[o] = fbar[o] * act'(pre2[o]) on lane o (< 6)
+    const float tl = (e.l < 6) ? gbuf[swz(i * 6 + e.l, e.m)] * d2 : 0.0f;
+    float t[6];
+#pragma unroll
+    for (int o = 0; o < 6; ++o) t[o] = grp_get(tl, o, e);
+    // s1[k] = (sum_o t[o] W2[o][k]) * act'(pre1[k]) for this lane's hidden units k = l, 8+l
+    const int ka = e.l, kb = min(8 + e.l, 9);
+    float ga = 0.0f, gb = 0.0f;
+#pragma unroll
+    for (int o = 0; o < 6; ++o) {
+        ga = fmaf(t[o], w2[o * 10 + ka], ga);
+        gb = fmaf(t[o], w2[o * 10 + kb], gb);
+    }
+    ga *= d1a;
+    gb *= d1b;
+    float s1[10];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s1[k] = grp_get(ga, k, e);
+    s1[8] = grp_get(gb, 0, e);
+    s1[9] = grp_get(gb, 1, e);
+    const int ja = ROOT ? min(e.l, 3) : e.l, jb = min(8 + e.l, 9);
+    ua = 0.0f; ub = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        ua = fmaf(s1[k], w1[k * fin + ja], ua);
+        if (!ROOT) ub = fmaf(s1[k], w1[k * fin + jb], ub);
+    }
+}
+template <bool ROOT>
+__device__ __forceinline__ void bone_backward_write(float* gbuf, int i, const EncLane& e, float ua, float ub) {
+    const int par = c_parent[i];
+    if (e.l < 4) {
+        gbuf[swz(128 + i * 4 + e.l, e.m)] = ua;
+    } else if (!ROOT) {
+        gbuf[swz(par * 6 + (e.l - 4), e.m)] += ua;
+    }
+    if (!ROOT && e.l < 2) gbuf[swz(par * 6 + 4 + e.l, e.m)] += ub;
+}
+template <bool SOFT, bool RA, bool RB>
+__device__ __forceinline__ void enc_bwd_pair(const float* encw, const float* qs, const float* feat, float* gbuf, const EncLane& e,
+                                             float apar, int ia, int ib) {
+    float uaa, uab, uba, ubb;
+    bone_backward<SOFT, RA>(encw, qs, feat, gbuf, ia, e, apar, uaa, uab);
+    bone_backward<SOFT, RB>(encw, qs, feat, gbuf, ib, e, apar, uba, ubb);
+    bone_backward_write<RA>(gbuf, ia, e, uaa, uab);     // the two joints of a pair never share a parent
+    bone_backward_write<RB>(gbuf, ib, e, uba, ubb);
+    __syncwarp();
+}
+
+// reverse encoder: features in `feat`, feature gradients in rows [0,126) of `gbuf` (accumulated in place; the schedule is
+// the forward one reversed, a reverse topological order), quaternion gradients -> rows [128+e] of `gbuf`.
 template <bool SOFT>
 __device__ __forceinline__ void encoder_backward(const float* encw, const float* qs, const float* feat, float* gbuf,
                                                  const EncLane& e, float apar) {
-    for (int i = 20; i >= 0; --i) {
-        const int par = c_parent[i];
-        const bool root = par < 0;
-        const int fin = root ? 4 : 10;
-        const float* w = encw + enc_off(i);
-        float u[10], h[10], f, d1a, d1b, d2;
-        bone_forward<SOFT>(w, root, qs, feat, i, par, e, apar, u, h, f, d1a, d1b, d2);
-        const float* w1 = w;
-        const float* w2 = w + 10 * fin + 10;
-        // t[o] = fbar[o] * act'(pre2[o]) on lane o (< 6)
-        const float tl = (e.l < 6) ? gbuf[swz(i * 6 + e.l, e.m)] * d2 : 0.0f;
-        float t[6];
-#pragma unroll
-        for (int o = 0; o < 6; ++o) t[o] = grp_get(tl, o, e);
-        // s1[k] = (sum_o t[o] W2[o][k]) * act'(pre1[k]) for this lane's hidden units k = l, 8+l
-        const int ka = e.l, kb = min(8 + e.l, 9);
-        float ga = 0.0f, gb = 0.0f;
-#pragma unroll
-        for (int o = 0; o < 6; ++o) {
-            ga = fmaf(t[o], w2[o * 10 + ka], ga);
-            gb = fmaf(t[o], w2[o * 10 + kb], gb);
-        }
-        ga *= d1a;
-        gb *= d1b;
-        float s1[10];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s1[k] = grp_get(ga, k, e);
-        s1[8] = grp_get(gb, 0, e);
-        s1[9] = grp_get(gb, 1, e);
-        // ubar[j] = sum_k s1[k] W1[k][j] for this lane's inputs j = l (and 8+l for l < 2, non-root)
-        const int ja = root ? min(e.l, 3) : e.l, jb = min(8 + e.l, 9);
-        float ua = 0.0f, ub = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            ua = fmaf(s1[k], w1[k * fin + ja], ua);
-            if (!root) ub = fmaf(s1[k], w1[k * fin + jb], ub);
-        }
-        if (e.l < 4) {
-            gbuf[swz(128 + i * 4 + e.l, e.m)] = ua;
-        } else if (!root) {
-            gbuf[swz(par * 6 + (e.l - 4), e.m)] += ua;
-        }
-        if (!root && e.l < 2) gbuf[swz(par * 6 + 4 + e.l, e.m)] += ub;
+    for (int i = 20; i >= 18; --i) {
+        float ua, ub;
+        bone_backward<SOFT, false>(encw, qs, feat, gbuf, i, e, apar, ua, ub);
+        bone_backward_write<false>(gbuf, i, e, ua, ub);
         __syncwarp();
     }
+    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 17, 15);
+    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 16, 13);
+    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 14, 11);
+    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 12, 10);
+    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 9, 8);
+    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 7, 6);
+    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 5, 4);
+    enc_bwd_pair<SOFT, false, true>(encw, qs, feat, gbuf, e, apar, 3, 2);
+    enc_bwd_pair<SOFT, true, true>(encw, qs, feat, gbuf, e, apar, 1, 0);
 }
 
 // pytorch3d 0.7.2 axis_angle_to_quaternion (formula restated; source not in the reference tree)
