@@ -65,6 +65,11 @@ int pndf_param_count(const pndf_config* cfg, size_t* n);
  * The library repacks it into the slab stream the kernel consumes and uploads it (synchronous). */
 int pndf_set_weights(pndf_handle* h, const float* flat, size_t n);
 
+/* The same for a DEVICE pointer (the trainer's parameters after optimizer.step(), model/train_posendf.py:99):
+ * the repacking is a gather kernel enqueued on `stream`, no host round trip, no synchronisation.  Launches that
+ * use the handle afterwards must be ordered after it (same stream or an event). */
+int pndf_set_weights_device(pndf_handle* h, const float* flat_dev, size_t n, void* stream);
+
 /* PoseNDF.forward(pose, train=False)['dist_pred']  (model/posendf.py:62-76,100-101).
  * normalise != 0 applies F.normalize(pose, dim=1) (posendf.py:71); normalise == 0 is the manifold
  * branch of the train path (posendf.py:80-83).  dist_dev: B floats. */

@@ -26,6 +26,7 @@ SYMBOLS = {
     "pndf_destroy": (C.c_int, [C.c_void_p]),
     "pndf_param_count": (C.c_int, [C.POINTER(PndfConfig), C.POINTER(C.c_size_t)]),
     "pndf_set_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pndf_set_weights_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "pndf_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "pndf_forward_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pndf_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

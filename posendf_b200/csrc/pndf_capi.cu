@@ -39,6 +39,14 @@ struct pndf_handle {
     float* d_wstream = nullptr;   // slab stream
     size_t wstream_floats = 0;
     float* d_small = nullptr;     // biases (2625) + w6 (64) + encoder (3516), each 16B-aligned
+    size_t small_floats = 0;
+    // device-side packing: slab stream / small buffer element -> index into the flat parameter vector (-1 = zero pad)
+    int32_t* d_map_w = nullptr;
+    int32_t* d_map_s = nullptr;
+    float* d_flat = nullptr;      // staging copy of the flat parameter vector (host uploads)
+    cudaEvent_t w_event = nullptr; // recorded after the last repack; launches on other streams wait for it
+    cudaStream_t w_stream = nullptr;
+    bool w_pending = false;
     size_t off_bias[7];
     size_t off_w6 = 0, off_enc = 0;
     float* d_scratch = nullptr;   // softplus derivative scratch, num_sms * kUnits * 32 floats
@@ -105,6 +113,115 @@ void pack_op(std::vector<float>& out, int K, int TN, int KG, F get) {
         }
 }
 
+// Lay the flat parameter vector (reference state_dict order) out as (slab stream, small-parameter buffer) and record the
+// offsets in the handle.  Run once at create time on the vector 1,2,3,... so that the result is an index map; the
+// actual packing of weights is then a device-side gather (pack_gather_kernel), which keeps a training step free of
+// host round trips.
+int build_streams(pndf_handle* h, const float* flat, std::vector<float>& s, std::vector<float>& sm) {
+    const float* enc = nullptr;
+    const float* cur = flat;
+    if (h->cfg.use_enc) {
+        enc = cur;
+        cur += kEncFloats;
+    }
+    const int in0 = h->cfg.in_dim;
+    const int widths[8] = {in0, 256, 512, 1024, 512, 256, 64, 1};
+    const float* W[7];
+    const float* Bv[7];
+    for (int l = 0; l < 7; ++l) {
+        W[l] = cur; cur += (size_t)widths[l + 1] * widths[l];
+        Bv[l] = cur; cur += widths[l + 1];
+    }
+    // ---- slab stream, in consumption order (pndf_kernel.cuh)
+    s.clear();
+    s.reserve((size_t)340 * kWarps * kSlabFloats);
+    auto fwd = [&](int l, int k_off, int n_off) {   // w(k,n) = W_l[n_off+n][k_off+k]
+        const float* w = W[l]; const int in = widths[l], out = widths[l + 1];
+        return [=](int k, int n) { return (k_off + k < in && n_off + n < out) ? w[(size_t)(n_off + n) * in + (k_off + k)] : 0.0f; };
+    };
+    auto bwd = [&](int l, int k_off, int n_off) {   // w(k,n) = W_l[k_off+k][n_off+n]
+        const float* w = W[l]; const int in = widths[l], out = widths[l + 1];
+        return [=](int k, int n) { return (k_off + k < out && n_off + n < in) ? w[(size_t)(k_off + k) * in + (n_off + n)] : 0.0f; };
+    };
+    pack_op(s, h->z0_rows, 8, 2, fwd(0, 0, 0));   // F0  (N = 256, split-K)
+    pack_op(s, 256, 8, 1, fwd(1, 0, 0));          // F1
+    pack_op(s, 512, 8, 1, fwd(2, 0, 0));          // F2a : out features [0,512)
+    pack_op(s, 512, 8, 1, fwd(3, 0, 0));          // F3a : in  features [0,512)
+    pack_op(s, 512, 8, 1, fwd(2, 0, 512));        // F2b : out features [512,1024)
+    pack_op(s, 512, 8, 1, fwd(3, 512, 0));        // F3b : in  features [512,1024)
+    pack_op(s, 512, 8, 2, fwd(4, 0, 0));          // F4  (N = 256, split-K)
+    pack_op(s, 256, 1, 1, fwd(5, 0, 0));          // F5  (N = 64)
+    pack_op(s, 64, 8, 2, bwd(5, 0, 0));           // B5  (N = 256, split-K)
+    pack_op(s, 256, 8, 1, bwd(4, 0, 0));          // B4
+    pack_op(s, 512, 8, 1, bwd(3, 0, 0));          // B3a : in  features [0,512) of layer 3
+    pack_op(s, 512, 8, 1, bwd(2, 0, 0));          // B2a : out features [0,512) of layer 2
+    pack_op(s, 512, 8, 1, bwd(3, 0, 512));        // B3b
+    pack_op(s, 512, 8, 1, bwd(2, 512, 0));        // B2b
+    pack_op(s, 512, 8, 2, bwd(1, 0, 0));          // B1  (N = 256, split-K)
+    pack_op(s, 256, 2, 1, bwd(0, 0, 0));          // B0  (N = 128: in_dim padded)
+    const size_t expect = (size_t)(h->f0_slabs + 2 * slabs_of(256, 1, 64) + 8 * slabs_of(512, 1, 64) + 2 * slabs_of(512, 2, 64) +
+                                   slabs_of(256, 1, 8) + slabs_of(64, 2, 64) + slabs_of(256, 1, 16)) * kWarps * kSlabFloats;
+    if (s.size() != expect) return fail("internal: slab stream size mismatch");
+    // ---- small parameters
+    sm.clear();
+    auto align4 = [&]() { while (sm.size() % 4) sm.push_back(0.0f); };
+    for (int l = 0; l < 7; ++l) {
+        align4();
+        h->off_bias[l] = sm.size();
+        sm.insert(sm.end(), Bv[l], Bv[l] + widths[l + 1]);
+    }
+    align4(); h->off_w6 = sm.size(); sm.insert(sm.end(), W[6], W[6] + 64);
+    align4(); h->off_enc = sm.size();
+    if (enc) sm.insert(sm.end(), enc, enc + kEncFloats);
+    align4();
+    return 0;
+}
+
+__global__ void pack_gather_kernel(const float* __restrict__ flat, const int32_t* __restrict__ map, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int32_t m = map[i];
+        out[i] = (m >= 0) ? flat[m] : 0.0f;
+    }
+}
+
+int pack_on_device(pndf_handle* h, const float* d_flat, cudaStream_t st) {
+    pack_gather_kernel<<<h->num_sms * 4, 256, 0, st>>>(d_flat, h->d_map_w, h->d_wstream, h->wstream_floats);
+    pack_gather_kernel<<<8, 256, 0, st>>>(d_flat, h->d_map_s, h->d_small, h->small_floats);
+    CUDA_OK(cudaGetLastError());
+    if (!h->w_event) CUDA_OK(cudaEventCreateWithFlags(&h->w_event, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(h->w_event, st));
+    h->w_stream = st;
+    h->w_pending = true;
+    h->have_weights = true;
+    return 0;
+}
+
+// a launch on a stream other than the one the weights were last repacked on has to wait for that repack
+int order_after_weights(pndf_handle* h, cudaStream_t st) {
+    if (h->w_pending && st != h->w_stream) CUDA_OK(cudaStreamWaitEvent(st, h->w_event, 0));
+    return 0;
+}
+
+int build_maps(pndf_handle* h) {
+    const size_t n = param_count(&h->cfg);
+    std::vector<float> iota(n), s, sm;
+    for (size_t i = 0; i < n; ++i) iota[i] = (float)(i + 1);      // exact in fp32 (n < 2^24); 0 marks padding
+    if (build_streams(h, iota.data(), s, sm)) return 1;
+    std::vector<int32_t> mw(s.size()), ms(sm.size());
+    for (size_t i = 0; i < s.size(); ++i) mw[i] = (int32_t)s[i] - 1;
+    for (size_t i = 0; i < sm.size(); ++i) ms[i] = (int32_t)sm[i] - 1;
+    h->wstream_floats = s.size();
+    h->small_floats = sm.size();
+    CUDA_OK(cudaMalloc(&h->d_wstream, s.size() * sizeof(float)));
+    CUDA_OK(cudaMalloc(&h->d_small, sm.size() * sizeof(float)));
+    CUDA_OK(cudaMalloc(&h->d_map_w, mw.size() * sizeof(int32_t)));
+    CUDA_OK(cudaMalloc(&h->d_map_s, ms.size() * sizeof(int32_t)));
+    CUDA_OK(cudaMalloc(&h->d_flat, n * sizeof(float)));
+    CUDA_OK(cudaMemcpy(h->d_map_w, mw.data(), mw.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(h->d_map_s, ms.data(), ms.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st) {
     if (!h->have_weights) return fail("pndf_set_weights has not been called");
     if (p.B <= 0) return 0;
@@ -119,6 +236,7 @@ int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st) {
     p.enc_beta = h->cfg.enc_beta; p.df_beta = h->cfg.df_beta;
     p.f0_slabs = h->f0_slabs; p.z0_rows = h->z0_rows; p.in_dim = h->cfg.in_dim;
     const int grid = std::min(p.ntiles, h->num_sms);
+    if (order_after_weights(h, st)) return 1;
     if (mode == 1)
         pndf_fused_kernel<1><<<grid, kThreads, kSmTotal, st>>>(p);
     else if (mode == 2)
@@ -164,6 +282,7 @@ int pndf_create(const pndf_config* cfg, pndf_handle** out) {
     CUDA_OK(cudaMalloc(&h->d_z0, (size_t)h->num_sms * 128 * 32 * sizeof(float)));
     if (cfg->df_act == PNDF_ACT_SOFTPLUS)
         CUDA_OK(cudaMalloc(&h->d_scratch, (size_t)h->num_sms * kUnits * 32 * sizeof(float)));
+    if (build_maps(h)) { pndf_destroy(h); return 1; }
     *out = h;
     return 0;
 }
@@ -173,6 +292,10 @@ int pndf_destroy(pndf_handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_wstream);
     cudaFree(h->d_small);
+    cudaFree(h->d_map_w);
+    cudaFree(h->d_map_s);
+    cudaFree(h->d_flat);
+    if (h->w_event) cudaEventDestroy(h->w_event);
     cudaFree(h->d_scratch);
     cudaFree(h->d_z0);
     for (int i = 0; i < 4; ++i) cudaFree(h->d_dn[i]);
@@ -189,69 +312,17 @@ int pndf_set_weights(pndf_handle* h, const float* flat, size_t n) {
     if (!h || !flat) return fail("null argument");
     if (n != param_count(&h->cfg)) return fail("pndf_set_weights: wrong parameter count");
     CUDA_OK(cudaSetDevice(h->cfg.device));
-    const float* enc = nullptr;
-    const float* cur = flat;
-    if (h->cfg.use_enc) {
-        enc = cur;
-        cur += kEncFloats;
-    }
-    const int in0 = h->cfg.in_dim;
-    const int widths[8] = {in0, 256, 512, 1024, 512, 256, 64, 1};
-    const float* W[7];
-    const float* Bv[7];
-    for (int l = 0; l < 7; ++l) {
-        W[l] = cur; cur += (size_t)widths[l + 1] * widths[l];
-        Bv[l] = cur; cur += widths[l + 1];
-    }
-    // ---- slab stream, in consumption order (pndf_kernel.cuh)
-    std::vector<float> s;
-    s.reserve((size_t)340 * kWarps * kSlabFloats);
-    auto fwd = [&](int l, int k_off, int n_off) {   // w(k,n) = W_l[n_off+n][k_off+k]
-        const float* w = W[l]; const int in = widths[l], out = widths[l + 1];
-        return [=](int k, int n) { return (k_off + k < in && n_off + n < out) ? w[(size_t)(n_off + n) * in + (k_off + k)] : 0.0f; };
-    };
-    auto bwd = [&](int l, int k_off, int n_off) {   // w(k,n) = W_l[k_off+k][n_off+n]
-        const float* w = W[l]; const int in = widths[l], out = widths[l + 1];
-        return [=](int k, int n) { return (k_off + k < out && n_off + n < in) ? w[(size_t)(k_off + k) * in + (n_off + n)] : 0.0f; };
-    };
-    pack_op(s, h->z0_rows, 8, 2, fwd(0, 0, 0));   // F0  (N = 256, split-K)
-    pack_op(s, 256, 8, 1, fwd(1, 0, 0));          // F1
-    pack_op(s, 512, 8, 1, fwd(2, 0, 0));          // F2a : out features [0,512)
-    pack_op(s, 512, 8, 1, fwd(3, 0, 0));          // F3a : in  features [0,512)
-    pack_op(s, 512, 8, 1, fwd(2, 0, 512));        // F2b : out features [512,1024)
-    pack_op(s, 512, 8, 1, fwd(3, 512, 0));        // F3b : in  features [512,1024)
-    pack_op(s, 512, 8, 2, fwd(4, 0, 0));          // F4  (N = 256, split-K)
-    pack_op(s, 256, 1, 1, fwd(5, 0, 0));          // F5  (N = 64)
-    pack_op(s, 64, 8, 2, bwd(5, 0, 0));           // B5  (N = 256, split-K)
-    pack_op(s, 256, 8, 1, bwd(4, 0, 0));          // B4
-    pack_op(s, 512, 8, 1, bwd(3, 0, 0));          // B3a : in  features [0,512) of layer 3
-    pack_op(s, 512, 8, 1, bwd(2, 0, 0));          // B2a : out features [0,512) of layer 2
-    pack_op(s, 512, 8, 1, bwd(3, 0, 512));        // B3b
-    pack_op(s, 512, 8, 1, bwd(2, 512, 0));        // B2b
-    pack_op(s, 512, 8, 2, bwd(1, 0, 0));          // B1  (N = 256, split-K)
-    pack_op(s, 256, 2, 1, bwd(0, 0, 0));          // B0  (N = 128: in_dim padded)
-    const size_t expect = (size_t)(h->f0_slabs + 2 * slabs_of(256, 1, 64) + 8 * slabs_of(512, 1, 64) + 2 * slabs_of(512, 2, 64) +
-                                   slabs_of(256, 1, 8) + slabs_of(64, 2, 64) + slabs_of(256, 1, 16)) * kWarps * kSlabFloats;
-    if (s.size() != expect) return fail("internal: slab stream size mismatch");
-    // ---- small parameters
-    std::vector<float> sm;
-    auto align4 = [&]() { while (sm.size() % 4) sm.push_back(0.0f); };
-    for (int l = 0; l < 7; ++l) {
-        align4();
-        h->off_bias[l] = sm.size();
-        sm.insert(sm.end(), Bv[l], Bv[l] + widths[l + 1]);
-    }
-    align4(); h->off_w6 = sm.size(); sm.insert(sm.end(), W[6], W[6] + 64);
-    align4(); h->off_enc = sm.size();
-    if (enc) sm.insert(sm.end(), enc, enc + kEncFloats);
-    align4();
-    if (!h->d_wstream) CUDA_OK(cudaMalloc(&h->d_wstream, s.size() * sizeof(float)));
-    if (!h->d_small) CUDA_OK(cudaMalloc(&h->d_small, sm.size() * sizeof(float)));
-    h->wstream_floats = s.size();
-    CUDA_OK(cudaMemcpy(h->d_wstream, s.data(), s.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMemcpy(h->d_small, sm.data(), sm.size() * sizeof(float), cudaMemcpyHostToDevice));
-    h->have_weights = true;
+    CUDA_OK(cudaMemcpy(h->d_flat, flat, n * sizeof(float), cudaMemcpyHostToDevice));
+    if (pack_on_device(h, h->d_flat, nullptr)) return 1;
+    CUDA_OK(cudaStreamSynchronize(nullptr));
     return 0;
+}
+
+int pndf_set_weights_device(pndf_handle* h, const float* flat_dev, size_t n, void* stream) {
+    if (!h || !flat_dev) return fail("null argument");
+    if (n != param_count(&h->cfg)) return fail("pndf_set_weights_device: wrong parameter count");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    return pack_on_device(h, flat_dev, (cudaStream_t)stream);
 }
 
 int pndf_forward(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, float* dist_dev, void* stream) {
@@ -429,6 +500,7 @@ int pndf_encoder_tangent(pndf_handle* h, const float* pose_dev, const float* v_d
     EncTrainParams p{};
     p.x = pose_dev; p.v = v_dev; p.encw = h->d_small + h->off_enc; p.zdot_tiles = zdot_tiles_dev; p.B = B;
     p.normalise = normalise; p.act = h->cfg.enc_act; p.beta = h->cfg.enc_beta; p.use_enc = h->cfg.use_enc;
+    if (order_after_weights(h, (cudaStream_t)stream)) return 1;
     enc_tangent_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
     CUDA_OK(cudaGetLastError());
     h->launches++;
@@ -450,6 +522,7 @@ int pndf_encoder_param_grads(pndf_handle* h, const float* pose_dev, const float*
     p.x = pose_dev; p.v = v_dev; p.encw = h->d_small + h->off_enc; p.up1 = up_first_dev; p.upt = up_tangent_dev;
     p.upz = up_second_dev; p.grads = grads_dev; p.B = B; p.normalise = normalise; p.act = h->cfg.enc_act;
     p.beta = h->cfg.enc_beta; p.use_enc = 1;
+    if (order_after_weights(h, st)) return 1;
     enc_grad_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(p);
     CUDA_OK(cudaGetLastError());
     h->launches++;

@@ -130,11 +130,60 @@ __global__ void __launch_bounds__(128) enc_tangent_kernel(const EncTrainParams p
     out[127 * 32] = 0.0f;
 }
 
-// warp-reduce v, lane 0 adds it into the block accumulator
-__device__ __forceinline__ void red_add(float* acc, float v, int lane) {
+// Transposing warp reduction: every lane holds 32 values v[0..31]; afterwards lane L holds sum over lanes of v[L].
+// 31 shuffles per 32 values (a plain butterfly per value would need 160), all of a stage independent of each other.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) atomicAdd(acc, v);
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float keep = up ? v[j + half] : v[j];
+            const float send = up ? v[j] : v[j + half];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+// per-pose adjoints of one joint (set 0: first-order objective; set 1: Eikonal objective, value + tangent adjoints)
+struct BoneAdj {
+    float p2b0[6], p2b1[6], p2db1[6];
+    float p1b0[10], p1b1[10], p1db1[10];
+};
+
+// e-th parameter of a joint in the reference's own order (W1 [10][fin], b1 [10], W2 [6][10], b2 [6]): this pose's term
+template <bool ROOT, int SET>
+__device__ __forceinline__ float bone_grad_entry(int e, const BoneState& s, const BoneAdj& a) {
+    constexpr int fin = ROOT ? 4 : 10;
+    if (e < 10 * fin) {
+        const int o = e / fin, k = e % fin;
+        return SET == 0 ? a.p1b0[o] * s.u[k] : fmaf(a.p1b1[o], s.u[k], a.p1db1[o] * s.ud[k]);
+    }
+    e -= 10 * fin;
+    if (e < 10) return SET == 0 ? a.p1b0[e] : a.p1b1[e];
+    e -= 10;
+    if (e < 60) {
+        const int o = e / 10, k = e % 10;
+        return SET == 0 ? a.p2b0[o] * s.h[k] : fmaf(a.p2b1[o], s.h[k], a.p2db1[o] * s.hd[k]);
+    }
+    e -= 60;
+    if (e < 6) return SET == 0 ? a.p2b0[e] : a.p2b1[e];
+    return 0.0f;
+}
+
+// reduce this joint's parameter-gradient terms over the warp and add them to the block accumulator `acc` (shared)
+template <bool ROOT, int SET>
+__device__ __forceinline__ void bone_grad_reduce(float* acc, const BoneState& s, const BoneAdj& a, int lane) {
+    constexpr int n = ROOT ? 116 : 176;
+#pragma unroll
+    for (int g = 0; g < (n + 31) / 32; ++g) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = bone_grad_entry<ROOT, SET>(g * 32 + j, s, a);
+        const float tot = warp_transpose_sum(v, lane);
+        if (g * 32 + lane < n) atomicAdd(acc + g * 32 + lane, tot);
+    }
 }
 
 __global__ void __launch_bounds__(128) enc_grad_kernel(const EncTrainParams p) {
@@ -145,6 +194,7 @@ __global__ void __launch_bounds__(128) enc_grad_kernel(const EncTrainParams p) {
     const bool live = b < p.B;
     const long long bb = live ? b : 0;
     const int lane = threadIdx.x & 31;
+    const bool set1 = (p.upt != nullptr) || (p.upz != nullptr);     // uniform: the Eikonal objective is present
     float q[84], qd[84], feat[21][6], featd[21][6];
     load_q_qd(p, bb, q, qd);
     for (int i = 0; i < 21; ++i) {
@@ -172,58 +222,57 @@ __global__ void __launch_bounds__(128) enc_grad_kernel(const EncTrainParams p) {
         const float* w2 = w1 + 10 * fin + 10;
         BoneState s;
         bone_fwd_tan(p.encw + off, i, par, q, qd, feat, featd, p.act, p.beta, s);
-        float* a0 = acc + off;
-        float* a1 = acc + kEncFloats + off;
+        BoneAdj a;
         // layer 2
-        float p2b0[6], p2b1[6], p2db1[6];
 #pragma unroll
         for (int o = 0; o < 6; ++o) {
-            p2b0[o] = fb0[i][o] * s.d1f[o];
-            p2db1[o] = fdb1[i][o] * s.d1f[o];
-            p2b1[o] = fb1[i][o] * s.d1f[o] + fdb1[i][o] * s.d2f[o] * s.p2d[o];
+            a.p2b0[o] = fb0[i][o] * s.d1f[o];
+            a.p2db1[o] = fdb1[i][o] * s.d1f[o];
+            a.p2b1[o] = fb1[i][o] * s.d1f[o] + fdb1[i][o] * s.d2f[o] * s.p2d[o];
         }
         float hb0[10], hb1[10], hdb1[10];
 #pragma unroll
         for (int k = 0; k < 10; ++k) { hb0[k] = 0.0f; hb1[k] = 0.0f; hdb1[k] = 0.0f; }
-        for (int o = 0; o < 6; ++o) {
+#pragma unroll
+        for (int o = 0; o < 6; ++o)
 #pragma unroll
             for (int k = 0; k < 10; ++k) {
                 const float ww = __ldg(w2 + o * 10 + k);
-                hb0[k] = fmaf(ww, p2b0[o], hb0[k]); hb1[k] = fmaf(ww, p2b1[o], hb1[k]); hdb1[k] = fmaf(ww, p2db1[o], hdb1[k]);
-                red_add(a0 + 10 * fin + 10 + o * 10 + k, p2b0[o] * s.h[k], lane);
-                red_add(a1 + 10 * fin + 10 + o * 10 + k, p2b1[o] * s.h[k] + p2db1[o] * s.hd[k], lane);
+                hb0[k] = fmaf(ww, a.p2b0[o], hb0[k]); hb1[k] = fmaf(ww, a.p2b1[o], hb1[k]); hdb1[k] = fmaf(ww, a.p2db1[o], hdb1[k]);
             }
-            red_add(a0 + 10 * fin + 70 + o, p2b0[o], lane);
-            red_add(a1 + 10 * fin + 70 + o, p2b1[o], lane);
-        }
         // layer 1
-        float p1b0[10], p1b1[10], p1db1[10];
 #pragma unroll
         for (int o = 0; o < 10; ++o) {
-            p1b0[o] = hb0[o] * s.d1h[o];
-            p1db1[o] = hdb1[o] * s.d1h[o];
-            p1b1[o] = hb1[o] * s.d1h[o] + hdb1[o] * s.d2h[o] * s.p1d[o];
-        }
-        float ub0[10], ub1[10], udb1[10];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) { ub0[k] = 0.0f; ub1[k] = 0.0f; udb1[k] = 0.0f; }
-        for (int o = 0; o < 10; ++o) {
-            for (int k = 0; k < fin; ++k) {
-                const float ww = __ldg(w1 + o * fin + k);
-                ub0[k] = fmaf(ww, p1b0[o], ub0[k]); ub1[k] = fmaf(ww, p1b1[o], ub1[k]); udb1[k] = fmaf(ww, p1db1[o], udb1[k]);
-                red_add(a0 + o * fin + k, p1b0[o] * s.u[k], lane);
-                red_add(a1 + o * fin + k, p1b1[o] * s.u[k] + p1db1[o] * s.ud[k], lane);
-            }
-            red_add(a0 + 10 * fin + o, p1b0[o], lane);
-            red_add(a1 + 10 * fin + o, p1b1[o], lane);
+            a.p1b0[o] = hb0[o] * s.d1h[o];
+            a.p1db1[o] = hdb1[o] * s.d1h[o];
+            a.p1b1[o] = hb1[o] * s.d1h[o] + hdb1[o] * s.d2h[o] * s.p1d[o];
         }
         if (!root) {
+            float ub0[6], ub1[6], udb1[6];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) { fb0[par][r] += ub0[4 + r]; fb1[par][r] += ub1[4 + r]; fdb1[par][r] += udb1[4 + r]; }
+            for (int r = 0; r < 6; ++r) { ub0[r] = 0.0f; ub1[r] = 0.0f; udb1[r] = 0.0f; }
+#pragma unroll
+            for (int o = 0; o < 10; ++o)
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const float ww = __ldg(w1 + o * 10 + 4 + r);
+                    ub0[r] = fmaf(ww, a.p1b0[o], ub0[r]); ub1[r] = fmaf(ww, a.p1b1[o], ub1[r]); udb1[r] = fmaf(ww, a.p1db1[o], udb1[r]);
+                }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) { fb0[par][r] += ub0[r]; fb1[par][r] += ub1[r]; fdb1[par][r] += udb1[r]; }
+        }
+        // parameter gradients of this joint, reduced over the 32 poses of the warp
+        if (root) {
+            bone_grad_reduce<true, 0>(acc + off, s, a, lane);
+            if (set1) bone_grad_reduce<true, 1>(acc + kEncFloats + off, s, a, lane);
+        } else {
+            bone_grad_reduce<false, 0>(acc + off, s, a, lane);
+            if (set1) bone_grad_reduce<false, 1>(acc + kEncFloats + off, s, a, lane);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * kEncFloats; i += blockDim.x) atomicAdd(p.grads + i, acc[i]);
+    const int nacc = set1 ? 2 * kEncFloats : kEncFloats;
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) atomicAdd(p.grads + i, acc[i]);
 }
 
 }  // namespace pndf

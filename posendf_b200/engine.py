@@ -46,6 +46,12 @@ class Engine:
         flat = np.ascontiguousarray(np.asarray(flat, dtype=np.float32).reshape(-1))
         _lib.check(self.lib.pndf_set_weights(self._h, flat.ctypes.data_as(C.c_void_p), flat.size))
 
+    def set_weights_device(self, flat):
+        """flat fp32 CUDA tensor in state_dict order; repacked by a gather kernel on the current stream (no host sync)"""
+        flat = self._prep(flat, 1)
+        _lib.check(self.lib.pndf_set_weights_device(self._h, flat.data_ptr(), flat.numel(), _stream_ptr(self.device)))
+        self._flat_keepalive = flat     # the gather may still be in flight when the caller drops its reference
+
     # ---- helpers
     def _prep(self, t, last):
         if not (isinstance(t, torch.Tensor) and t.is_cuda and t.device == self.device):

@@ -8,8 +8,11 @@ What runs where
     pre-activation adjoint  a_l = d d / d pre_l  (launch 1, also for the manifold batch without normalisation), and
     the forward-mode tangents  zdot_l  of all layer inputs along a given input tangent (launch 2, Eikonal term).
     That is 99.8 % of the per-sample arithmetic (the 7-layer DFNet chain, three times).
-  * cuBLAS through torch.mm (plain library GEMMs, fp32):  the batch reductions
-        dW_l = sum_b  a_l[b] (x) (delta_b z_l[b] + zdot_l[b])   (+ second-order term for softplus)
+  * cuBLAS through torch.mm / torch.bmm (plain library GEMMs, fp32, explicit split-K for the small layers):  the
+    batch reductions
+        dW_l = sum_b  a_l[b] (x) (w_d delta_b z_l[b] + w_e zdot_l[b])   (+ second-order term for softplus)
+    They run in backward(), when the upstream weights w_d / w_m / w_e of the three losses are known, so that the
+    distance and the Eikonal term of the pose batch share ONE GEMM per layer (the manifold batch has its own adjoints).
   * two small one-thread-per-pose kernels for the 3 516-parameter structure encoder (0.2 % of the arithmetic):
     pndf_encoder_tangent (input tangent of launch 2) and pndf_encoder_param_grads (reverse sweep of the encoder for
     the first-order and the Eikonal objective incl. the softplus second-derivative terms).  No torch autograd anywhere.
@@ -32,41 +35,53 @@ import torch
 from . import _lib
 
 DUMP_ROWS = 5504
-# layer inputs z_0..z_6: (row offset, width); z_0 is 126 wide with the encoder, 84 without (rows padded to 128)
+# export columns (pose-major dump, DESIGN.md "export column map"):
+#   layer inputs z_0..z_6 at [0, 2752): (offset, width); z_0 is 126 wide with the encoder, 84 without (padded to 128)
 Z_ROWS = [(0, None), (128, 256), (384, 512), (896, 1024), (1920, 512), (2432, 256), (2688, 64)]
-# adjoints of the pre-activations pre_0..pre_5 (pre_l feeds z_{l+1}); pre_6 is the scalar s
+Z_END = 2752
+#   adjoints of the pre-activations pre_0..pre_5 at [2752, 5376) (pre_l feeds z_{l+1}); pre_6 is the scalar s
 A_ROWS = [(5120, 256), (4608, 512), (3584, 1024), (3072, 512), (2816, 256), (2752, 64)]
+A_END = 5376
 G0_ROW = 5376
-CHUNK = 65536      # poses per export chunk (bounds the dump buffers at ~1.4 GB each)
+CHUNK = 65536      # poses per export launch (one dump buffer = 1.4 GB at this size)
+ENC_FLOATS = 3516
+# explicit split-K factors of the weight-gradient GEMMs (tools/tune_wgrad.py on a B200, K = 32 768 poses): the outputs are
+# only 2 .. 32 tiles of 128x128, far fewer than 148 SMs
+_SPLIT_K = {0: 64, 1: 16, 2: 8, 3: 8, 4: 16, 5: 64}
 
 
-def _rows(dump, r0, n, B):
-    """dump (Bpad, 5504) pose-major -> strided (B, n) view of columns [r0, r0+n) (no copy; cuBLAS takes the stride)"""
-    return dump[:B, r0:r0 + n]
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
 
 
 class _Exports:
+    """launch 1 on one chunk of poses: distances, pose gradient and the pose-major dump of every layer input / adjoint"""
+
     def __init__(self, eng, x, normalise):
         B = x.shape[0]
         T = (B + 31) // 32
-        self.B = B
+        self.B, self.x, self.normalise = B, x, normalise
         self.dump = torch.empty(T * 32, DUMP_ROWS, device=x.device, dtype=torch.float32)
         self.dist = torch.empty(B, 1, device=x.device, dtype=torch.float32)
         self.grad = torch.empty(B, 21, 4, device=x.device, dtype=torch.float32)
         _lib.check(eng.lib.pndf_forward_grad_export(eng._h, x.data_ptr(), B, int(normalise), self.dist.data_ptr(),
-                                                    self.grad.data_ptr(), self.dump.data_ptr(),
-                                                    torch.cuda.current_stream(x.device).cuda_stream))
+                                                    self.grad.data_ptr(), self.dump.data_ptr(), _stream(x)))
+        self.delta = None      # d loss / d dist per pose for unit upstream weight, (B,)
+        self.v = None          # dE/dg, the pose tangent of the Eikonal term
+        self.dump_t = None     # launch 2 export (tangents of the layer inputs)
 
-    def z(self, l, in_dim):
-        r0, n = Z_ROWS[l]
-        return _rows(self.dump, r0, in_dim if l == 0 else n, self.B)
+    def cols(self, c0, n):
+        """strided (B, n) view of dump columns [c0, c0+n) -- no copy, cuBLAS takes the row stride"""
+        return self.dump[:self.B, c0:c0 + n]
 
-    def a(self, l):
-        r0, n = A_ROWS[l]
-        return _rows(self.dump, r0, n, self.B)
-
-    def g0(self, in_dim):
-        return _rows(self.dump, G0_ROW, in_dim, self.B)
+    def tangent_launch(self, eng):
+        x, B = self.x, self.B
+        tan = torch.zeros((B + 31) // 32, 128, 32, device=x.device, dtype=torch.float32)
+        _lib.check(eng.lib.pndf_encoder_tangent(eng._h, x.data_ptr(), self.v.data_ptr(), B, int(self.normalise), tan.data_ptr(),
+                                                _stream(x)))
+        self.dump_t = torch.empty(tan.shape[0] * 32, DUMP_ROWS, device=x.device, dtype=torch.float32)
+        _lib.check(eng.lib.pndf_forward_tangent_export(eng._h, x.data_ptr(), B, int(self.normalise), tan.data_ptr(),
+                                                       self.dump_t.data_ptr(), _stream(x)))
 
 
 def _out_act_deriv(d, act, beta):
@@ -75,31 +90,13 @@ def _out_act_deriv(d, act, beta):
         sig = -torch.expm1(-beta * d)               # sigma(beta s) = 1 - exp(-beta d), accurate for tiny d
         return sig, beta * sig * (1.0 - sig)
     pos = (d > 0).to(d.dtype)
-    return pos, torch.zeros_like(d)
+    return pos, None
 
 
-def _hidden_act_deriv(z_next, act, beta):
-    """phi'(pre_l) and phi''(pre_l)/phi'(pre_l) recovered from z_{l+1} = phi(pre_l)."""
-    if act == "softplus":
-        sig = -torch.expm1(-beta * z_next)           # phi' = sigma(beta pre) = 1 - exp(-beta z), accurate for tiny z
-        return sig, beta * (1.0 - sig)
-    slope = 0.0 if act == "relu" else 0.01
-    return torch.where(z_next > 0, torch.ones_like(z_next), torch.full_like(z_next, slope)), None
-
-
-ENC_FLOATS = 3516
-
-
-def _stream(t):
-    return torch.cuda.current_stream(t.device).cuda_stream
-
-
-def _encoder_tangent(eng, x, v, normalise):
-    """tangent of the DFNet input along the pose tangent v, already in the [tile][128][32] layout of launch 2"""
-    B = x.shape[0]
-    tiles = torch.zeros((B + 31) // 32, 128, 32, device=x.device, dtype=torch.float32)
-    _lib.check(eng.lib.pndf_encoder_tangent(eng._h, x.data_ptr(), v.data_ptr(), B, int(normalise), tiles.data_ptr(), _stream(x)))
-    return tiles
+def _hidden_act_deriv(z_next, beta):
+    """softplus: phi'(pre_l) and phi''(pre_l)/phi'(pre_l) recovered from z_{l+1} = phi(pre_l)."""
+    sig = -torch.expm1(-beta * z_next)               # phi' = sigma(beta pre) = 1 - exp(-beta z), accurate for tiny z
+    return sig, beta * (1.0 - sig)
 
 
 def _encoder_param_grads(eng, x, v, normalise, up1, upt, upz):
@@ -109,6 +106,15 @@ def _encoder_param_grads(eng, x, v, normalise, up1, upt, upz):
     _lib.check(eng.lib.pndf_encoder_param_grads(eng._h, x.data_ptr(), ptr(v), x.shape[0], int(normalise), ptr(up1), ptr(upt),
                                                 ptr(upz), out.data_ptr(), _stream(x)))
     return out
+
+
+def _wgrad(view, a, r, split):
+    """view (n_out, n_in) += a^T r  with a (B, n_out), r (B, n_in) row-strided; split-K over the poses through bmm"""
+    B = a.shape[0]
+    if split > 1 and B % split == 0 and B // split >= 512:
+        view.add_(torch.bmm(a.unflatten(0, (split, B // split)).transpose(1, 2), r.unflatten(0, (split, B // split))).sum(0))
+    else:
+        view.addmm_(a.t(), r)
 
 
 class _FlatGrads:
@@ -122,136 +128,128 @@ class _FlatGrads:
         for n, p in ps:
             self.views[n] = self.flat[off:off + p.numel()].view(p.shape)
             off += p.numel()
+        self.has_enc = any(n.startswith("enc.") for n, _ in ps)
 
-    def addmm(self, name, a_t, b):          # view += a_t @ b
-        self.views[name].addmm_(a_t, b)
+    def W(self, l):
+        return self.views[f"dfnet.lin{l}.weight"]
 
-    def add(self, name, val):
-        v = self.views[name]
-        v.add_(val.reshape(v.shape))
-
-    def add_encoder(self, flat3516):
-        self.flat[:ENC_FLOATS].add_(flat3516)
+    def b(self, l):
+        return self.views[f"dfnet.lin{l}.bias"]
 
 
-def fused_param_grads(net, x, delta_fn, normalise=True, eik_weight=None, loss_norm=None):
-    """Parameter gradients of  sum_b delta[b] * d(x[b])  (+ those of the Eikonal term if eik_weight is not None), the
-    distances and the Eikonal value.  x (B,21,4) fp32 CUDA; delta_fn(dist_chunk, lo, hi) -> (hi-lo,) upstream gradient
-    on d for poses [lo,hi) (evaluated after the distances are known, so no extra forward launch is needed).  Returns
-    (first-order _FlatGrads, Eikonal _FlatGrads or None, dist (B,1), eikonal scalar or None)."""
-    eng = net.engine()
+def _accumulate(out, net, eng, ex, up, w_eik):
+    """out += up * d/dtheta sum_b delta_b d(x_b)  (+ w_eik * d/dtheta Eikonal term if ex carries a tangent export).
+    up, w_eik are 0-dim device tensors (the upstream gradients of the losses); nothing here synchronises."""
     cfg = net._cfg
     in_dim, act, beta = cfg["in_dim"], cfg["df_act"], cfg["df_beta"]
-    W = [getattr(net.dfnet, f"lin{l}").weight.detach() for l in range(7)]
-    old_tf32 = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = False
-    try:
-        g1, ge = _FlatGrads(net), (_FlatGrads(net) if eik_weight is not None else None)
-        dists, eik_sum = [], x.new_zeros(())
-        Btot = x.shape[0]
-        for c0 in range(0, Btot, CHUNK):
-            xc = x[c0:c0 + CHUNK].contiguous()
-            ex = _Exports(eng, xc, normalise)
-            dists.append(ex.dist)
-            dl = delta_fn(ex.dist, c0, c0 + xc.shape[0]).reshape(-1, 1)
-            gs, gss = _out_act_deriv(ex.dist, act, beta)                    # (B,1)
-            A = [ex.a(l) for l in range(6)]
-            Z = [ex.z(l, in_dim) for l in range(7)]
-            # ---- first-order term: dW_l = (delta * a_l)^T z_l
-            for l in range(6):
-                da = dl * A[l]
-                g1.addmm(f"dfnet.lin{l}.weight", da.t(), Z[l])
-                g1.add(f"dfnet.lin{l}.bias", da.sum(0))
-            g1.add("dfnet.lin6.weight", ((dl * gs) * Z[6]).sum(0))
-            g1.add("dfnet.lin6.bias", (dl * gs).sum(0))
-            g0 = ex.g0(in_dim).contiguous()                                  # adjoint of the encoder output (unit upstream)
-            up0 = dl * g0
-            if eik_weight is None:
-                if net.enc is not None:
-                    g1.add_encoder(_encoder_param_grads(eng, xc, None, normalise, up0, None, None)[0])
-                continue
-            # ---- Eikonal term
-            g = ex.grad
-            nrm = g.norm(2, dim=-1, keepdim=True)
-            count = float((loss_norm if loss_norm is not None else Btot) * 21)
-            eik_sum = eik_sum + ((nrm - 1) ** 2).sum()
-            v = ((2.0 * (nrm - 1) / count) * (g / nrm)).contiguous()         # dE/dg  (mean over all (b,j))
-            tan = _encoder_tangent(eng, xc, v, normalise)
-            dump_t = torch.empty(tan.shape[0] * 32, DUMP_ROWS, device=xc.device, dtype=torch.float32)
-            _lib.check(eng.lib.pndf_forward_tangent_export(eng._h, xc.data_ptr(), ex.B, int(normalise), tan.data_ptr(),
-                                                           dump_t.data_ptr(), _stream(xc)))
-            Zd = [_rows(dump_t, 0, in_dim, ex.B)] + [_rows(dump_t, Z_ROWS[l][0], Z_ROWS[l][1], ex.B) for l in range(1, 7)]
-            for l in range(6):
-                ge.addmm(f"dfnet.lin{l}.weight", A[l].t(), Zd[l])
-            ge.add("dfnet.lin6.weight", (gs * Zd[6]).sum(0))
-            up_z0 = None
-            if act == "softplus":
-                # second-order adjoint chain (phi'' != 0): seven GEMMs on the exported tensors
-                sdot = Zd[6] @ W[6].t()                                      # (B,1)
-                pbar = gss * sdot                                            # adjoint of s
-                ge.add("dfnet.lin6.weight", (pbar * Z[6]).sum(0))
-                ge.add("dfnet.lin6.bias", pbar.sum(0))
-                zbar = pbar @ W[6]                                           # (B,64) adjoint of z_6
-                for l in range(5, -1, -1):
-                    d1, ratio = _hidden_act_deriv(Z[l + 1], act, beta)       # phi'(pre_l), phi''/phi'
-                    pdot = Zd[l + 1] / d1.clamp_min(1e-30)                   # tangent of pre_l
-                    pbar = zbar * d1 + A[l] * ratio * pdot                   # A[l] = gbar_{l+1} * phi'
-                    ge.addmm(f"dfnet.lin{l}.weight", pbar.t(), Z[l])
-                    ge.add(f"dfnet.lin{l}.bias", pbar.sum(0))
-                    zbar = pbar @ W[l]
-                up_z0 = zbar.contiguous()
-            if net.enc is not None:
-                eg = _encoder_param_grads(eng, xc, v, normalise, up0, g0, up_z0)
-                g1.add_encoder(eg[0])
-                ge.add_encoder(eg[1])
-        dist = torch.cat(dists, 0) if len(dists) > 1 else dists[0]
-        eik = None
-        if eik_weight is not None:
-            eik = eik_sum / float((loss_norm if loss_norm is not None else Btot) * 21)
-        return g1, ge, dist, eik
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+    B = ex.B
+    eik = w_eik is not None and ex.dump_t is not None
+    coef = (up * ex.delta).reshape(B, 1)
+    # right-hand sides of all layers at once: R = coef * z (+ w_eik * zdot)
+    R = ex.cols(0, Z_END) * coef
+    if eik:
+        R.addcmul_(ex.dump_t[:B, :Z_END], w_eik)
+    for l in range(6):
+        n_in = in_dim if l == 0 else Z_ROWS[l][1]
+        _wgrad(out.W(l), ex.cols(*A_ROWS[l]), R[:, Z_ROWS[l][0]:Z_ROWS[l][0] + n_in], _SPLIT_K[l])
+    # biases of lin0..5: coef^T a_l, all layers in one GEMV over the adjoint columns (a_5 first, a_0 last)
+    ball = (coef.t() @ ex.cols(Z_END, A_END - Z_END)).reshape(-1)
+    for l in range(6):
+        c0 = A_ROWS[l][0] - Z_END
+        out.b(l).add_(ball[c0:c0 + A_ROWS[l][1]])
+    gs, gss = _out_act_deriv(ex.dist, act, beta)                                  # (B,1)
+    out.W(6).add_(gs.t() @ R[:, Z_ROWS[6][0]:Z_END])
+    out.b(6).add_((coef * gs).sum().reshape(1))
+    g0 = ex.cols(G0_ROW, in_dim)                                                   # dd/dz0 per pose
+    up1 = (coef * g0).contiguous()
+    upt = upz = None
+    if eik:
+        upt = (w_eik * g0).contiguous()
+        if act == "softplus":
+            # second-order adjoint chain (phi'' != 0), scaled by w_eik from its seed on
+            W = [getattr(net.dfnet, f"lin{l}").weight.detach() for l in range(7)]
+            Z = [ex.cols(Z_ROWS[l][0], in_dim if l == 0 else Z_ROWS[l][1]) for l in range(7)]
+            Zd = [ex.dump_t[:B, Z_ROWS[l][0]:Z_ROWS[l][0] + Z_ROWS[l][1]] for l in range(1, 7)]     # tangents of z_1..z_6
+            pbar = (w_eik * gss) * (Zd[5] @ W[6].t())                              # adjoint of s, (B,1)
+            out.W(6).add_(pbar.t() @ Z[6])
+            out.b(6).add_(pbar.sum().reshape(1))
+            zbar = pbar @ W[6]                                                     # (B,64) adjoint of z_6
+            for l in range(5, -1, -1):
+                d1, ratio = _hidden_act_deriv(Z[l + 1], beta)                      # phi'(pre_l), phi''/phi'
+                pdot = Zd[l] / d1.clamp_min(1e-30)                                 # tangent of pre_l
+                pbar = zbar * d1 + (w_eik * ratio) * ex.cols(*A_ROWS[l]) * pdot    # A[l] = gbar_{l+1} * phi'
+                _wgrad(out.W(l), pbar, Z[l], _SPLIT_K[l])
+                out.b(l).add_(pbar.sum(0))
+                zbar = pbar @ W[l]
+            upz = zbar.contiguous()
+    if out.has_enc:
+        eg = _encoder_param_grads(eng, ex.x, ex.v if eik else None, ex.normalise, up1, upt, upz)
+        out.flat[:ENC_FLOATS].add_(eg[0])
+        if eik:
+            out.flat[:ENC_FLOATS].add_(eg[1])
 
 
 class FusedTrainLosses(torch.autograd.Function):
-    """(dist loss, manifold loss, Eikonal loss) of model/posendf.py:85-96 with parameter gradients from the fused path.
-    backward() combines the three per-term gradient vectors with the upstream weights (model/train_posendf.py:95-98)."""
+    """(dist loss, manifold loss, Eikonal loss) of model/posendf.py:85-96.  forward() runs the fused launches and keeps
+    their exports; backward() turns them into the parameter gradients for the upstream weights it is handed
+    (model/train_posendf.py:95-98).  Memory: 22 KB per exported pose and launch (three launches per pose/manifold pair)."""
 
     @staticmethod
     def forward(ctx, net, pose, dist_gt, man_poses, loss_type, want_eik, *params):
+        eng = net.engine()
         B = pose.shape[0]
-
-        def delta_dist(dist, lo, hi):
-            diff = dist[:, 0] - dist_gt[lo:hi]
-            return torch.sign(diff) / B if loss_type == "l1" else 2.0 * diff / B
-
-        g_dist, g_eik, d, eik = fused_param_grads(net, pose, delta_dist, True, 1.0 if want_eik else None)
+        pose_ex, man_ex = [], []
+        eik_sum = pose.new_zeros(())
+        for c0 in range(0, B, CHUNK):
+            ex = _Exports(eng, pose[c0:c0 + CHUNK], True)
+            diff = ex.dist[:, 0] - dist_gt[c0:c0 + ex.B]
+            ex.delta = torch.sign(diff) / B if loss_type == "l1" else 2.0 * diff / B
+            if want_eik:
+                nrm = ex.grad.norm(2, dim=-1, keepdim=True)
+                eik_sum = eik_sum + ((nrm - 1) ** 2).sum()
+                ex.v = ((2.0 * (nrm - 1) / float(B * 21)) * (ex.grad / nrm)).contiguous()   # dE/dg (mean over all (b,j))
+                ex.tangent_launch(eng)
+            ex.grad = None
+            pose_ex.append(ex)
+        d = torch.cat([e.dist for e in pose_ex], 0) if len(pose_ex) > 1 else pose_ex[0].dist
         diff = d[:, 0] - dist_gt
         loss_d = diff.abs().mean() if loss_type == "l1" else (diff * diff).mean()
-        g_man, loss_m = None, loss_d.new_zeros(())
+        loss_m, eik = loss_d.new_zeros(()), loss_d.new_zeros(())
         if want_eik:     # the reference only reports / trains the manifold term together with the Eikonal term (posendf.py:94-99)
             Bm = man_poses.shape[0]
-            g_man, _, dm, _ = fused_param_grads(net, man_poses, lambda dist, lo, hi: torch.sign(dist[:, 0]) / Bm, False, None)
-            loss_m = dm.abs().mean()
-        ctx.flats = [g.flat if g is not None else None for g in (g_dist, g_man, g_eik)]
+            msum = loss_d.new_zeros(())
+            for c0 in range(0, Bm, CHUNK):
+                ex = _Exports(eng, man_poses[c0:c0 + CHUNK], False)
+                ex.delta = torch.sign(ex.dist[:, 0]) / Bm
+                ex.grad = None
+                msum = msum + ex.dist.abs().sum()
+                man_ex.append(ex)
+            loss_m = msum / Bm
+            eik = eik_sum / float(B * 21)
+        ctx.net, ctx.eng, ctx.pose_ex, ctx.man_ex = net, eng, pose_ex, man_ex
         ctx.shapes = [p.shape for p in params]
-        if not want_eik:
-            eik = loss_d.new_zeros(())
         return loss_d, loss_m, eik
 
     @staticmethod
     def backward(ctx, gd, gm, ge):
-        tot = None
-        for up, flat in zip((gd, gm, ge), ctx.flats):
-            if flat is None or up is None:
-                continue
-            tot = up * flat if tot is None else tot.add_(up * flat)
-        out, off = [], 0
+        net, eng = ctx.net, ctx.eng
+        out = _FlatGrads(net)
+        old_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            for ex in ctx.pose_ex:
+                _accumulate(out, net, eng, ex, gd, ge)
+            for ex in ctx.man_ex:
+                _accumulate(out, net, eng, ex, gm, None)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = old_tf32
+        ctx.pose_ex = ctx.man_ex = None
+        grads, off = [], 0
         for shp in ctx.shapes:
             n = shp.numel()
-            out.append(tot[off:off + n].view(shp))
+            grads.append(out.flat[off:off + n].view(shp))
             off += n
-        return (None, None, None, None, None, None, *out)
+        return (None, None, None, None, None, None, *grads)
 
 
 def train_forward(net, pose, dist_gt, man_poses, eikonal):

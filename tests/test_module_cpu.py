@@ -58,11 +58,20 @@ def test_eval_forward_on_cpu_fails_loudly():
         net(torch.zeros(2, 21, 4), train=False)
 
 
+def test_train_forward_on_cpu_fails_loudly():
+    net = PoseNDF(make_opt())
+    with pytest.raises(RuntimeError, match="no CPU"):
+        net(torch.zeros(4, 21, 4), torch.zeros(4), torch.zeros(4, 21, 4), train=True, eikonal=1.0)
+
+
 def test_train_forward_matches_reference_losses():
-    """train=True is served by torch autograd over the same parameters: values must equal the reference's."""
+    """the torch-autograd cross-check mode (fused_train=False) that the GPU tests compare the fused train step with:
+    in fp64 on the CPU its values must equal the reference's."""
     from conftest import load_golden
     meta, z = load_golden("lrelu_enc_s1")
-    net = PoseNDF(make_opt()).double()
+    opt = make_opt()
+    opt["train"]["fused_train"] = False
+    net = PoseNDF(opt).double()
     net.load_state_dict({k: torch.from_numpy(v).double() for k, v in synth.make_params(1).items()})
     s = meta["seed"]
     tp = torch.from_numpy(synth.make_poses(2000 + s, 32, kind="noisy", sigma=0.25)).double()
