@@ -502,11 +502,22 @@ __device__ __forceinline__ void splitk_combine(float (&acc)[8][TN], float* out, 
 // strided (B x width) matrices, no repacking before the weight-gradient GEMMs).  `rows` is a multiple of 32 here, a warp
 // writes 32 consecutive features of one pose (coalesced); the transposed shared-memory read is 4-way bank conflicted,
 // which does not matter next to the GEMMs.
+// (rows is a multiple of 32.)  One warp iteration moves a 32-feature x 4-pose block with 8 lanes per pose row: lane
+// (pq, fl) reads features 4 fl .. 4 fl + 3 of pose 4 mq + pq (four scalar LDS, conflict-free under the swizzle) and writes
+// them with one 16-byte store, so a warp store covers four full 128-byte lines.  The stores are streaming (evict-first):
+// 22 KB per pose would otherwise push the L2-resident weight stream out of the cache -- measured on B200, 32 768 poses:
+// 3.89 ms with plain stores, 3.26 ms with st.global.cs, 3.21 ms without any export.
 __device__ __forceinline__ void dump_rows(float* dbg, int row0, const float* buf, int rows, int tid) {
     if (dbg == nullptr) return;
-    for (int idx = tid; idx < rows * 32; idx += kGemmThreads) {
-        const int m = idx / rows, r = idx - m * rows;
-        dbg[(size_t)m * kDumpRows + row0 + r] = buf[swz(r, m)];
+    const int warp = tid >> 5, lane = tid & 31;
+    const int pq = lane >> 3, fl = lane & 7;
+    const int nblk = (rows >> 5) * 8;
+    for (int c = warp; c < nblk; c += kWarps) {
+        const int r = ((c >> 3) << 5) + 4 * fl, m = (c & 7) * 4 + pq;
+        const float* src = buf + r * 32 + (((((m >> 2) ^ (r >> 2)) & 7) << 2) | (m & 3));
+        float4 v;
+        v.x = src[0]; v.y = src[32]; v.z = src[64]; v.w = src[96];
+        __stcs(reinterpret_cast<float4*>(dbg + (size_t)m * kDumpRows + row0 + r), v);
     }
 }
 

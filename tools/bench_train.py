@@ -24,11 +24,16 @@ for fused in (True, False):
         sum(ld.values()).backward()
         optim.step()
         return ld
-    step(); torch.cuda.synchronize()
-    t0 = time.perf_counter(); n = 3
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter(); n = 10
+    e0.record()
     for _ in range(n): ld = step()
+    e1.record()
     torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / n
-    out["fused" if fused else "torch_autograd"] = {"ms_per_step": dt * 1e3, "samples_per_s": B / dt, "losses": {k: float(v) for k, v in ld.items()},
+    out["fused" if fused else "torch_autograd"] = {"ms_per_step": dt * 1e3, "ms_per_step_device": e0.elapsed_time(e1) / n,
+                                                     "samples_per_s": B / dt, "losses": {k: float(v) for k, v in ld.items()},
                                                      "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9}
     torch.cuda.reset_peak_memory_stats()
 print(json.dumps(out))
