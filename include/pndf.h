@@ -125,11 +125,15 @@ int pndf_forward_grad_debug(pndf_handle* h, const float* pose_dev, int64_t B, in
  * dW_l = sum_b adj_l[b] (x) z_l[b].
  * pndf_forward_tangent_export recomputes the forward pass and then pushes the tangent tan_dev[t][128][32] of the DFNet
  * input through the linearised network (forward mode), exporting the tangents of all layer inputs to columns
- * [0,2752) of dump_dev[b]: the second operand of the Eikonal term's weight gradients. */
+ * [0,2752) of dump_dev[b]: the second operand of the Eikonal term's weight gradients.
+ * act_masks_dev (nullable, pndf_act_mask_bytes(B) bytes): for a relu / lrelu DFNet launch 1 stores the 1-bit activation
+ * derivatives of every hidden unit there (10.6 KB per 32 poses) and the tangent launch, given the same buffer, skips
+ * its own primal forward pass (half of its arithmetic).  Ignored for a softplus DFNet (fp32 derivatives). */
+int pndf_act_mask_bytes(int64_t B, size_t* n);
 int pndf_forward_grad_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, float* dist_dev, float* grad_dev,
-                             float* dump_dev, void* stream);
+                             float* dump_dev, void* act_masks_dev, void* stream);
 int pndf_forward_tangent_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, const float* tan_dev,
-                                float* dump_dev, void* stream);
+                                float* dump_dev, const void* act_masks_dev, void* stream);
 
 /* Structure-encoder side of the training step (model/network/net_modules.py:140-170, 3 516 parameters).
  * pndf_encoder_tangent: tangent of the encoder output (or of the normalised pose without encoder) along the pose

@@ -466,8 +466,14 @@ int pndf_forward_grad_debug(pndf_handle* h, const float* pose_dev, int64_t B, in
     return launch(h, p, 1, (cudaStream_t)stream);
 }
 
+int pndf_act_mask_bytes(int64_t B, size_t* n) {
+    if (B < 0 || !n) return fail("bad argument");
+    *n = (size_t)((B + kTileM - 1) / kTileM) * 4 * kMaskStride;
+    return 0;
+}
+
 int pndf_forward_grad_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, float* dist_dev, float* grad_dev,
-                             float* dump_dev, void* stream) {
+                             float* dump_dev, void* act_masks_dev, void* stream) {
     if (!h) return fail("null handle");
     if (B == 0) return 0;
     if (B < 0 || !pose_dev || !grad_dev || !dump_dev) return fail("null argument");
@@ -475,11 +481,13 @@ int pndf_forward_grad_export(pndf_handle* h, const float* pose_dev, int64_t B, i
     KParams p{};
     p.pose_in = pose_dev; p.dist = dist_dev; p.grad = grad_dev; p.B = B; p.steps = 1;
     p.normalise = normalise; p.input_kind = IN_QUAT; p.dbg = dump_dev; p.dump_all = 1;
+    // a softplus DFNet keeps fp32 derivatives in a per-CTA scratch instead of bit masks: nothing to hand over
+    p.act_masks = (h->cfg.df_act == PNDF_ACT_SOFTPLUS) ? nullptr : (uint8_t*)act_masks_dev;
     return launch(h, p, 1, (cudaStream_t)stream);
 }
 
 int pndf_forward_tangent_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, const float* tan_dev,
-                                float* dump_dev, void* stream) {
+                                float* dump_dev, const void* act_masks_dev, void* stream) {
     if (!h) return fail("null handle");
     if (B == 0) return 0;
     if (B < 0 || !pose_dev || !tan_dev || !dump_dev) return fail("null argument");
@@ -487,6 +495,7 @@ int pndf_forward_tangent_export(pndf_handle* h, const float* pose_dev, int64_t B
     KParams p{};
     p.pose_in = pose_dev; p.B = B; p.steps = 1; p.normalise = normalise; p.input_kind = IN_QUAT;
     p.dbg = dump_dev; p.dump_all = 1; p.tan_in = tan_dev;
+    p.act_masks = (h->cfg.df_act == PNDF_ACT_SOFTPLUS) ? nullptr : (uint8_t*)act_masks_dev;
     return launch(h, p, 2, (cudaStream_t)stream);
 }
 

@@ -77,6 +77,7 @@ struct KParams {
     float* dscratch;          // per-CTA fp32 derivative scratch (softplus) or nullptr
     float* z0scratch;         // per-CTA stash of the encoder features (128 x 32 floats), L2 resident
     float* dbg;               // dump of every intermediate tile ([row][32 poses], kDumpRows rows per tile) or nullptr
+    uint8_t* act_masks;       // [tile][4][kMaskStride] derivative bit masks: MODE 1 writes them, MODE 2 reads them (and skips its primal pass)
     int dump_all;             // 0: first tile only (debug hook)   1: every tile (training: exports for the weight gradients)
     const float* tan_in;      // MODE 2: tangent of the DFNet input, [tile][128][32] floats
     long long B;
@@ -769,6 +770,9 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     constexpr int bwd_slabs = kSB5 + kS1 + 4 * kS23 + kS4 + kSB0;
     const int step_slabs = fwd_slabs + (kGrad ? bwd_slabs : 0);
     constexpr int kPasses = (MODE == 2) ? 2 : 1;   // MODE 2 replays the forward slab stream for the tangent pass
+    // ... unless launch 1 handed over its activation-derivative masks (relu / lrelu DFNet): then only the tangent pass runs
+    const bool tan_only = (MODE == 2) && (p.act_masks != nullptr);
+    const int pass0 = tan_only ? 1 : 0;
 
     // ------------------------------------------------------------------ compute warps
     Ctx c;
@@ -787,7 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     pipe.wsrc = reinterpret_cast<const char*>(p.wstream) + (size_t)warp * kSlabBytes;
     {
         const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        pipe.left = (uint32_t)my_tiles * (uint32_t)p.steps * (uint32_t)step_slabs * (uint32_t)kPasses;
+        pipe.left = (uint32_t)my_tiles * (uint32_t)p.steps * (uint32_t)step_slabs * (uint32_t)(kPasses - pass0);
         pipe.pos = 0;
         // prologue: fill both stages of this warp's ring
         refill(pipe, c, 0);
@@ -801,7 +805,10 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                      : (p.dump_all ? p.dbg + (size_t)tile * kDumpRows * 32 : (tile == 0 ? p.dbg : nullptr));
 
         // ---- load the pose tile (coalesced), zero-fill the tail
-        if (p.input_kind == IN_QUAT) {
+        if (tan_only) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.act_masks + (size_t)tile * (4 * kMaskStride));
+            for (int i = tid; i < 4 * kMaskStride / 16; i += kGemmThreads) reinterpret_cast<uint4*>(mask)[i] = __ldg(src + i);
+        } else if (p.input_kind == IN_QUAT) {
             const float* src = p.pose_in + pose0 * 84;
             for (int idx = tid; idx < kTileM * 84; idx += kGemmThreads) {
                 const int m = idx / 84, e = idx - m * 84;
@@ -820,7 +827,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 for (int cpt = 0; cpt < 4; ++cpt) xs[m * kXS + j * 4 + cpt] = (m < nvalid) ? q[cpt] : 0.0f;
             }
         }
-        if (p.use_enc) {
+        if (p.use_enc && !tan_only) {
             for (int i = tid; i < kEncFloats; i += kGemmThreads) encw[i] = __ldg(p.encw + i);
         }
         gemm_bar();
@@ -828,7 +835,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
         for (int st = 0; st < p.steps; ++st) {
             float* dbg_s = (st == 0) ? dbg : nullptr;
             // ---- column norms, q = x / n, encoder: 8 lanes per pose, 4 poses per warp
-            {
+            if (!tan_only) {
                 const int cpt = enc.l & 3, hf = enc.l >> 2;
                 if (p.normalise) {
                     float sq = 0.0f;
@@ -854,7 +861,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 }
             }
             gemm_bar();
-            for (int pass = 0; pass < kPasses; ++pass) {
+            for (int pass = pass0; pass < kPasses; ++pass) {
             const bool tangent = (MODE == 2) && (pass == 1);
             float* dbg_p = (MODE == 2) ? (tangent ? dbg_s : nullptr) : dbg_s;
             if (tangent) {   // the DFNet input tangent replaces z0; every op below becomes linear (no bias, act -> act')
@@ -938,6 +945,10 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             }
             if (MODE == 2) gemm_bar();   // X (z6 / its tangent) is reloaded by the next pass
             }  // passes
+            if (MODE == 1 && p.act_masks != nullptr && st == 0) {   // hand the derivative masks to the tangent launch
+                uint4* dst = reinterpret_cast<uint4*>(p.act_masks + (size_t)tile * (4 * kMaskStride));
+                for (int i = tid; i < 4 * kMaskStride / 16; i += kGemmThreads) dst[i] = reinterpret_cast<const uint4*>(mask)[i];
+            }
             if (!kGrad) {
                 gemm_bar();
                 continue;

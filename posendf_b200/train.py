@@ -45,6 +45,7 @@ A_END = 5376
 G0_ROW = 5376
 CHUNK = 65536      # poses per export launch (one dump buffer = 1.4 GB at this size)
 ENC_FLOATS = 3516
+MASK_BYTES_PER_TILE = 4 * 2656   # == pndf_act_mask_bytes(32)
 # explicit split-K factors of the weight-gradient GEMMs (tools/tune_wgrad.py on a B200, K = 32 768 poses): the outputs are
 # only 2 .. 32 tiles of 128x128, far fewer than 148 SMs
 _SPLIT_K = {0: 64, 1: 16, 2: 8, 3: 8, 4: 16, 5: 64}
@@ -57,15 +58,18 @@ def _stream(t):
 class _Exports:
     """launch 1 on one chunk of poses: distances, pose gradient and the pose-major dump of every layer input / adjoint"""
 
-    def __init__(self, eng, x, normalise):
+    def __init__(self, eng, x, normalise, want_masks=False):
         B = x.shape[0]
         T = (B + 31) // 32
         self.B, self.x, self.normalise = B, x, normalise
         self.dump = torch.empty(T * 32, DUMP_ROWS, device=x.device, dtype=torch.float32)
+        # activation-derivative bit masks of this launch: lets the tangent launch skip its primal pass (relu / lrelu)
+        self.masks = torch.empty(T * MASK_BYTES_PER_TILE, device=x.device, dtype=torch.uint8) if want_masks else None
         self.dist = torch.empty(B, 1, device=x.device, dtype=torch.float32)
         self.grad = torch.empty(B, 21, 4, device=x.device, dtype=torch.float32)
         _lib.check(eng.lib.pndf_forward_grad_export(eng._h, x.data_ptr(), B, int(normalise), self.dist.data_ptr(),
-                                                    self.grad.data_ptr(), self.dump.data_ptr(), _stream(x)))
+                                                    self.grad.data_ptr(), self.dump.data_ptr(),
+                                                    None if self.masks is None else self.masks.data_ptr(), _stream(x)))
         self.delta = None      # d loss / d dist per pose for unit upstream weight, (B,)
         self.v = None          # dE/dg, the pose tangent of the Eikonal term
         self.dump_t = None     # launch 2 export (tangents of the layer inputs)
@@ -81,7 +85,8 @@ class _Exports:
                                                 _stream(x)))
         self.dump_t = torch.empty(tan.shape[0] * 32, DUMP_ROWS, device=x.device, dtype=torch.float32)
         _lib.check(eng.lib.pndf_forward_tangent_export(eng._h, x.data_ptr(), B, int(self.normalise), tan.data_ptr(),
-                                                       self.dump_t.data_ptr(), _stream(x)))
+                                                       self.dump_t.data_ptr(),
+                                                       None if self.masks is None else self.masks.data_ptr(), _stream(x)))
 
 
 def _out_act_deriv(d, act, beta):
@@ -108,13 +113,20 @@ def _encoder_param_grads(eng, x, v, normalise, up1, upt, upz):
     return out
 
 
-def _wgrad(view, a, r, split):
-    """view (n_out, n_in) += a^T r  with a (B, n_out), r (B, n_in) row-strided; split-K over the poses through bmm"""
+def _wgrad(view, a, r, split, scale=None):
+    """view (n_out, n_in) += [scale *] a^T r  with a (B, n_out), r (B, n_in) row-strided; split-K over the poses through bmm"""
     B = a.shape[0]
     if split > 1 and B % split == 0 and B // split >= 512:
-        view.add_(torch.bmm(a.unflatten(0, (split, B // split)).transpose(1, 2), r.unflatten(0, (split, B // split))).sum(0))
-    else:
+        prod = torch.bmm(a.unflatten(0, (split, B // split)).transpose(1, 2), r.unflatten(0, (split, B // split))).sum(0)
+    elif scale is None:
         view.addmm_(a.t(), r)
+        return
+    else:
+        prod = a.t() @ r
+    if scale is None:
+        view.add_(prod)
+    else:
+        view.addcmul_(prod, scale)
 
 
 class _FlatGrads:
@@ -139,26 +151,42 @@ class _FlatGrads:
 
 def _accumulate(out, net, eng, ex, up, w_eik):
     """out += up * d/dtheta sum_b delta_b d(x_b)  (+ w_eik * d/dtheta Eikonal term if ex carries a tangent export).
-    up, w_eik are 0-dim device tensors (the upstream gradients of the losses); nothing here synchronises."""
+    up, w_eik are 0-dim device tensors (the upstream gradients of the losses); nothing here synchronises.
+    ex.delta is either a (B,) tensor or a python float (the same weight for every pose: the manifold term, whose
+    sign(d) is 1 wherever the adjoints are non-zero) -- then the exported layer inputs are used as they are."""
     cfg = net._cfg
     in_dim, act, beta = cfg["in_dim"], cfg["df_act"], cfg["df_beta"]
     B = ex.B
     eik = w_eik is not None and ex.dump_t is not None
-    coef = (up * ex.delta).reshape(B, 1)
-    # right-hand sides of all layers at once: R = coef * z (+ w_eik * zdot)
-    R = ex.cols(0, Z_END) * coef
-    if eik:
-        R.addcmul_(ex.dump_t[:B, :Z_END], w_eik)
+    uniform = not torch.is_tensor(ex.delta)
+    if uniform:
+        assert not eik
+        scale = up * ex.delta                      # 0-dim
+        coef = scale.reshape(1, 1)
+        R = ex.cols(0, Z_END)                      # strided view, no copy
+    else:
+        scale = None
+        coef = (up * ex.delta).reshape(B, 1)
+        # right-hand sides of all layers at once: R = coef * z (+ w_eik * zdot)
+        R = ex.cols(0, Z_END) * coef
+        if eik:
+            R.addcmul_(ex.dump_t[:B, :Z_END], w_eik)
     for l in range(6):
         n_in = in_dim if l == 0 else Z_ROWS[l][1]
-        _wgrad(out.W(l), ex.cols(*A_ROWS[l]), R[:, Z_ROWS[l][0]:Z_ROWS[l][0] + n_in], _SPLIT_K[l])
+        _wgrad(out.W(l), ex.cols(*A_ROWS[l]), R[:, Z_ROWS[l][0]:Z_ROWS[l][0] + n_in], _SPLIT_K[l], scale)
     # biases of lin0..5: coef^T a_l, all layers in one GEMV over the adjoint columns (a_5 first, a_0 last)
-    ball = (coef.t() @ ex.cols(Z_END, A_END - Z_END)).reshape(-1)
+    if uniform:
+        ball = ex.cols(Z_END, A_END - Z_END).sum(0) * scale
+    else:
+        ball = (coef.t() @ ex.cols(Z_END, A_END - Z_END)).reshape(-1)
     for l in range(6):
         c0 = A_ROWS[l][0] - Z_END
         out.b(l).add_(ball[c0:c0 + A_ROWS[l][1]])
     gs, gss = _out_act_deriv(ex.dist, act, beta)                                  # (B,1)
-    out.W(6).add_(gs.t() @ R[:, Z_ROWS[6][0]:Z_END])
+    if uniform:
+        out.W(6).addcmul_(gs.t() @ R[:, Z_ROWS[6][0]:Z_END], scale)
+    else:
+        out.W(6).add_(gs.t() @ R[:, Z_ROWS[6][0]:Z_END])
     out.b(6).add_((coef * gs).sum().reshape(1))
     g0 = ex.cols(G0_ROW, in_dim)                                                   # dd/dz0 per pose
     up1 = (coef * g0).contiguous()
@@ -201,7 +229,7 @@ class FusedTrainLosses(torch.autograd.Function):
         pose_ex, man_ex = [], []
         eik_sum = pose.new_zeros(())
         for c0 in range(0, B, CHUNK):
-            ex = _Exports(eng, pose[c0:c0 + CHUNK], True)
+            ex = _Exports(eng, pose[c0:c0 + CHUNK], True, want_masks=want_eik)
             diff = ex.dist[:, 0] - dist_gt[c0:c0 + ex.B]
             ex.delta = torch.sign(diff) / B if loss_type == "l1" else 2.0 * diff / B
             if want_eik:
@@ -220,7 +248,7 @@ class FusedTrainLosses(torch.autograd.Function):
             msum = loss_d.new_zeros(())
             for c0 in range(0, Bm, CHUNK):
                 ex = _Exports(eng, man_poses[c0:c0 + CHUNK], False)
-                ex.delta = torch.sign(ex.dist[:, 0]) / Bm
+                ex.delta = 1.0 / Bm            # sign(d) / Bm with d >= 0; where d == 0 the exported adjoints vanish
                 ex.grad = None
                 msum = msum + ex.dist.abs().sum()
                 man_ex.append(ex)

@@ -19,4 +19,4 @@ def t(fn, n=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 print(sys.argv[1:] , "plain fwd+grad %.3f ms" % t(lambda: eng.forward_grad(x)),
-      "export %.3f ms" % t(lambda: _lib.check(eng.lib.pndf_forward_grad_export(eng._h, x.data_ptr(), B, 1, dist.data_ptr(), grad.data_ptr(), dump.data_ptr(), st))))
+      "export %.3f ms" % t(lambda: _lib.check(eng.lib.pndf_forward_grad_export(eng._h, x.data_ptr(), B, 1, dist.data_ptr(), grad.data_ptr(), dump.data_ptr(), None, st))))
