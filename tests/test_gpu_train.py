@@ -100,3 +100,81 @@ def test_fused_train_step_equals_torch_autograd_path_and_adam_step_runs():
     assert abs(outs[0][0] - outs[1][0]) < 1e-3 * outs[1][0]
     for k in outs[0][1]:
         assert abs(outs[0][1][k] - outs[1][1][k]) < 1e-5 * max(1.0, abs(outs[1][1][k]))
+
+
+@pytest.mark.parametrize("act,B", [("lrelu", 32768), ("softplus", 8192)])
+def test_large_batch_split_k_path_matches_autograd_cross_check(act, B, monkeypatch):
+    """real batch sizes take the split-K bmm reductions and (with a small CHUNK) several export launches per batch:
+    every parameter gradient must agree with torch autograd over cuBLAS on the same GPU (fp32 both)."""
+    from posendf_b200 import PoseNDF, train
+    monkeypatch.setattr(train, "CHUNK", B // 2)
+    cfg = dict(use_enc=True, enc_act=act, enc_beta=100.0, df_act=act, df_beta=100.0)
+    params = synth.make_params(5)
+    tp, tgt, tm = _batch(5, B)
+    grads = []
+    for fused in (True, False):
+        net = PoseNDF(_opt(cfg, fused=fused))
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+        _, ld = net(torch.from_numpy(tp), torch.from_numpy(tgt), torch.from_numpy(tm), train=True, eikonal=1.0)
+        (1.0 * ld["dist"] + 0.5 * ld["man_loss"] + 2.0 * ld["eikonal"]).backward()
+        grads.append({n: p.grad.double().cpu() for n, p in net.named_parameters()})
+    worst = 0.0
+    for n in grads[0]:
+        err = (grads[0][n] - grads[1][n]).norm().item() / max(grads[1][n].norm().item(), 1e-12)
+        worst = max(worst, err)
+        # relu / lrelu: units on their kink flip between the two fp32 evaluations (observed 1e-4); softplus ~1e-6
+        assert err < (1e-3 if act != "softplus" else 2e-5), (n, err)
+    print(act, B, "worst per-tensor relative difference fused vs autograd", worst)
+
+
+def test_device_weight_repack_equals_host_upload_and_follows_optimizer_steps():
+    """pndf_set_weights_device (gather kernel, model/train_posendf.py:99 -> next forward) == pndf_set_weights bit for bit"""
+    from posendf_b200 import PoseNDF
+    from posendf_b200.engine import Engine
+    cfg = dict(use_enc=True, enc_act="lrelu", enc_beta=100.0, df_act="lrelu", df_beta=100.0)
+    params = synth.make_params(9)
+    flat = synth.flatten_params(params)
+    x = torch.from_numpy(synth.make_poses(9, 96)).cuda()
+    a, b = Engine(device=0, **{k: cfg[k] for k in ("enc_act", "df_act")}), Engine(device=0, **{k: cfg[k] for k in ("enc_act", "df_act")})
+    a.set_weights_flat(flat)
+    b.set_weights_device(torch.from_numpy(flat).cuda())
+    da, ga = a.forward_grad(x)
+    db, gb = b.forward_grad(x)
+    assert torch.equal(da, db) and torch.equal(ga, gb)
+    # the module re-packs after every optimizer step, on a side stream as well
+    net = PoseNDF(_opt(cfg))
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    opt = torch.optim.SGD(net.parameters(), lr=1e-2)
+    tp, tgt, tm = _batch(9, 64)
+    d0 = net(x, train=False)["dist_pred"].clone()
+    _, ld = net(torch.from_numpy(tp), torch.from_numpy(tgt), torch.from_numpy(tm), train=True, eikonal=1.0)
+    sum(ld.values()).backward()
+    opt.step()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        d1 = net(x, train=False)["dist_pred"].clone()
+    side.synchronize()
+    c = Engine(device=0, **{k: cfg[k] for k in ("enc_act", "df_act")})
+    c.set_weights_flat(np.concatenate([p.detach().cpu().numpy().ravel() for p in net.parameters()]))
+    assert torch.equal(d1, c.forward(x)) and not torch.equal(d0, d1)
+
+
+def test_tangent_launch_with_mask_handoff_equals_two_pass_tangent():
+    """pndf_forward_tangent_export given launch 1's bit masks (skips its primal pass) == the self-contained two-pass launch"""
+    from posendf_b200 import _lib, train
+    from posendf_b200.engine import Engine
+    eng = Engine(device=0, enc_act="lrelu", df_act="lrelu")
+    eng.set_weights_flat(synth.flatten_params(synth.make_params(4)))
+    B = 200
+    x = torch.from_numpy(synth.make_poses(4, B, kind="noisy", sigma=0.25)).cuda()
+    v = torch.from_numpy(synth.make_poses(40, B, kind="raw")).cuda() * 1e-3
+    outs = []
+    for want in (True, False):
+        ex = train._Exports(eng, x, True, want_masks=want)
+        ex.v = v.contiguous()
+        ex.tangent_launch(eng)
+        outs.append(ex.dump_t[:B, :train.Z_END].clone())
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    assert outs[0].abs().max().item() > 0
