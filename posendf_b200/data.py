@@ -38,8 +38,10 @@ class ResidentPoseData:
         self.device = torch.device(device)
         self.batch_size, self.num_pts, self.flip, self.fix_flip_bug = int(batch_size), int(num_pts), bool(flip), bool(fix_flip_bug)
         self.gen = torch.Generator(device=self.device)
+        self.host_gen = torch.Generator()       # host-side choices (file order, which AMASS file): no device sync per item
         if seed is not None:
             self.gen.manual_seed(int(seed))
+            self.host_gen.manual_seed(int(seed))
         self.pose, self.dist = [], []
         for f in data_files:
             z = np.load(f)
@@ -67,7 +69,8 @@ class ResidentPoseData:
         if self.flip:
             pose = quat_flip(pose)
         dist = self.dist[idx][rows]
-        amass_idx = int(self._randint(len(self.amass), 1)) if amass_idx is None else amass_idx
+        if amass_idx is None:
+            amass_idx = int(torch.randint(0, len(self.amass), (1,), generator=self.host_gen))
         amass_rows = self._randint(len(self.amass[amass_idx]), self.num_pts) if amass_rows is None else amass_rows
         man = self.amass[amass_idx][amass_rows]
         if self.flip:
@@ -75,7 +78,7 @@ class ResidentPoseData:
         return {"pose": pose, "dist": dist, "man_poses": man}
 
     def __iter__(self):
-        order = torch.randperm(len(self.pose), device=self.device, generator=self.gen).tolist()      # shuffle=True
+        order = torch.randperm(len(self.pose), generator=self.host_gen).tolist()                      # shuffle=True
         for b in range(len(self)):
             items = [self.item(i) for i in order[b * self.batch_size:(b + 1) * self.batch_size]]
             yield {k: torch.stack([it[k] for it in items]) for k in ("pose", "dist", "man_poses")}
