@@ -126,14 +126,24 @@ int pndf_forward_grad_debug(pndf_handle* h, const float* pose_dev, int64_t B, in
  * pndf_forward_tangent_export recomputes the forward pass and then pushes the tangent tan_dev[t][128][32] of the DFNet
  * input through the linearised network (forward mode), exporting the tangents of all layer inputs to columns
  * [0,2752) of dump_dev[b]: the second operand of the Eikonal term's weight gradients.
- * act_masks_dev (nullable, pndf_act_mask_bytes(B) bytes): for a relu / lrelu DFNet launch 1 stores the 1-bit activation
- * derivatives of every hidden unit there (10.6 KB per 32 poses) and the tangent launch, given the same buffer, skips
- * its own primal forward pass (half of its arithmetic).  Ignored for a softplus DFNet (fp32 derivatives). */
-int pndf_act_mask_bytes(int64_t B, size_t* n);
+ * act_handoff_dev (nullable, pndf_act_handoff_bytes(h, B) bytes): launch 1 stores the activation derivatives of every
+ * hidden unit there -- 1 bit per unit and pose for a relu / lrelu DFNet (10.6 KB per 32 poses), fp32 for softplus
+ * (10.5 KB per pose) -- and the tangent launch, given the same buffer, skips its own primal forward pass (half of its
+ * arithmetic). */
+int pndf_act_handoff_bytes(const pndf_handle* h, int64_t B, size_t* n);
 int pndf_forward_grad_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, float* dist_dev, float* grad_dev,
-                             float* dump_dev, void* act_masks_dev, void* stream);
+                             float* dump_dev, void* act_handoff_dev, void* stream);
 int pndf_forward_tangent_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, const float* tan_dev,
-                                float* dump_dev, const void* act_masks_dev, void* stream);
+                                float* dump_dev, const void* act_handoff_dev, void* stream);
+
+/* One element-wise step of the softplus second-order adjoint chain of the Eikonal term (the double backward of
+ * model/posendf.py:89-96 / model/train_posendf.py:98 for act: softplus):
+ *   pbar[b][j] = zbar[b][j] * s + w * beta (1 - s) * adj[b][j] * zdot_next[b][j] / s ,   s = 1 - exp(-beta z_next[b][j])
+ * z_next, zdot_next, adj are (B x n) column slices of the pose-major exports (row stride ld floats); zbar, pbar dense;
+ * w_eik_dev a device scalar (nullable = 1).  n and ld multiples of 4, pointers 16-byte aligned. */
+int pndf_softplus_adjoint(int device, const float* z_next_dev, const float* zdot_next_dev, const float* adj_dev, int64_t ld,
+                          const float* zbar_dev, const float* w_eik_dev, float beta, int64_t B, int n, float* pbar_dev,
+                          void* stream);
 
 /* Structure-encoder side of the training step (model/network/net_modules.py:140-170, 3 516 parameters).
  * pndf_encoder_tangent: tangent of the encoder output (or of the normalised pose without encoder) along the pose

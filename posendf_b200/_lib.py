@@ -35,7 +35,9 @@ SYMBOLS = {
     "pndf_denoise_prior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pndf_debug_dump_floats": (C.c_int, [C.POINTER(C.c_size_t)]),
     "pndf_forward_grad_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "pndf_act_mask_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
+    "pndf_softplus_adjoint": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
+                                        C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "pndf_act_handoff_bytes": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_size_t)]),
     "pndf_forward_grad_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pndf_forward_tangent_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pndf_encoder_tangent": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),

@@ -4,6 +4,7 @@
 #include "pndf_kernel.cuh"
 #include "pndf_denoise.cuh"
 #include "pndf_encoder_train.cuh"
+#include "pndf_train_ops.cuh"
 #include "pndf_knn.cuh"
 
 #include <algorithm>
@@ -466,14 +467,15 @@ int pndf_forward_grad_debug(pndf_handle* h, const float* pose_dev, int64_t B, in
     return launch(h, p, 1, (cudaStream_t)stream);
 }
 
-int pndf_act_mask_bytes(int64_t B, size_t* n) {
-    if (B < 0 || !n) return fail("bad argument");
-    *n = (size_t)((B + kTileM - 1) / kTileM) * 4 * kMaskStride;
+int pndf_act_handoff_bytes(const pndf_handle* h, int64_t B, size_t* n) {
+    if (!h || B < 0 || !n) return fail("bad argument");
+    const size_t tiles = (size_t)((B + kTileM - 1) / kTileM);
+    *n = tiles * (h->cfg.df_act == PNDF_ACT_SOFTPLUS ? (size_t)kUnits * 32 * sizeof(float) : (size_t)4 * kMaskStride);
     return 0;
 }
 
 int pndf_forward_grad_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, float* dist_dev, float* grad_dev,
-                             float* dump_dev, void* act_masks_dev, void* stream) {
+                             float* dump_dev, void* act_handoff_dev, void* stream) {
     if (!h) return fail("null handle");
     if (B == 0) return 0;
     if (B < 0 || !pose_dev || !grad_dev || !dump_dev) return fail("null argument");
@@ -481,13 +483,12 @@ int pndf_forward_grad_export(pndf_handle* h, const float* pose_dev, int64_t B, i
     KParams p{};
     p.pose_in = pose_dev; p.dist = dist_dev; p.grad = grad_dev; p.B = B; p.steps = 1;
     p.normalise = normalise; p.input_kind = IN_QUAT; p.dbg = dump_dev; p.dump_all = 1;
-    // a softplus DFNet keeps fp32 derivatives in a per-CTA scratch instead of bit masks: nothing to hand over
-    p.act_masks = (h->cfg.df_act == PNDF_ACT_SOFTPLUS) ? nullptr : (uint8_t*)act_masks_dev;
+    p.act_masks = (uint8_t*)act_handoff_dev;
     return launch(h, p, 1, (cudaStream_t)stream);
 }
 
 int pndf_forward_tangent_export(pndf_handle* h, const float* pose_dev, int64_t B, int normalise, const float* tan_dev,
-                                float* dump_dev, const void* act_masks_dev, void* stream) {
+                                float* dump_dev, const void* act_handoff_dev, void* stream) {
     if (!h) return fail("null handle");
     if (B == 0) return 0;
     if (B < 0 || !pose_dev || !tan_dev || !dump_dev) return fail("null argument");
@@ -495,7 +496,7 @@ int pndf_forward_tangent_export(pndf_handle* h, const float* pose_dev, int64_t B
     KParams p{};
     p.pose_in = pose_dev; p.B = B; p.steps = 1; p.normalise = normalise; p.input_kind = IN_QUAT;
     p.dbg = dump_dev; p.dump_all = 1; p.tan_in = tan_dev;
-    p.act_masks = (h->cfg.df_act == PNDF_ACT_SOFTPLUS) ? nullptr : (uint8_t*)act_masks_dev;
+    p.act_masks = (uint8_t*)act_handoff_dev;
     return launch(h, p, 2, (cudaStream_t)stream);
 }
 
@@ -535,6 +536,23 @@ int pndf_encoder_param_grads(pndf_handle* h, const float* pose_dev, const float*
     enc_grad_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(p);
     CUDA_OK(cudaGetLastError());
     h->launches++;
+    return 0;
+}
+
+int pndf_softplus_adjoint(int device, const float* z_next_dev, const float* zdot_next_dev, const float* adj_dev, int64_t ld,
+                          const float* zbar_dev, const float* w_eik_dev, float beta, int64_t B, int n, float* pbar_dev,
+                          void* stream) {
+    if (B == 0) return 0;
+    if (B < 0 || n <= 0 || (n & 3) || (ld & 3) || !z_next_dev || !zdot_next_dev || !adj_dev || !zbar_dev || !pbar_dev)
+        return fail("pndf_softplus_adjoint: bad argument");
+    CUDA_OK(cudaSetDevice(device));
+    SoftplusAdjParams p{};
+    p.z_next = z_next_dev; p.zdot_next = zdot_next_dev; p.adj = adj_dev; p.zbar = zbar_dev; p.w = w_eik_dev; p.pbar = pbar_dev;
+    p.ld = ld; p.B = B; p.n = n; p.beta = beta;
+    const long long total = B * (long long)(n >> 2);
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+    softplus_adjoint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -77,7 +77,8 @@ struct KParams {
     float* dscratch;          // per-CTA fp32 derivative scratch (softplus) or nullptr
     float* z0scratch;         // per-CTA stash of the encoder features (128 x 32 floats), L2 resident
     float* dbg;               // dump of every intermediate tile ([row][32 poses], kDumpRows rows per tile) or nullptr
-    uint8_t* act_masks;       // [tile][4][kMaskStride] derivative bit masks: MODE 1 writes them, MODE 2 reads them (and skips its primal pass)
+    uint8_t* act_masks;       // activation-derivative handoff, MODE 1 writes / MODE 2 reads (and skips its primal pass):
+                              // relu, lrelu: [tile][4][kMaskStride] bit masks; softplus: [tile][kUnits][32] fp32
     int dump_all;             // 0: first tile only (debug hook)   1: every tile (training: exports for the weight gradients)
     const float* tan_in;      // MODE 2: tangent of the DFNet input, [tile][128][32] floats
     long long B;
@@ -806,8 +807,12 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
 
         // ---- load the pose tile (coalesced), zero-fill the tail
         if (tan_only) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.act_masks + (size_t)tile * (4 * kMaskStride));
-            for (int i = tid; i < 4 * kMaskStride / 16; i += kGemmThreads) reinterpret_cast<uint4*>(mask)[i] = __ldg(src + i);
+            if (p.df_act == ACT_SOFTPLUS) {
+                c.dscr = reinterpret_cast<float*>(p.act_masks) + (size_t)tile * kUnits * 32;
+            } else {
+                const uint4* src = reinterpret_cast<const uint4*>(p.act_masks + (size_t)tile * (4 * kMaskStride));
+                for (int i = tid; i < 4 * kMaskStride / 16; i += kGemmThreads) reinterpret_cast<uint4*>(mask)[i] = __ldg(src + i);
+            }
         } else if (p.input_kind == IN_QUAT) {
             const float* src = p.pose_in + pose0 * 84;
             for (int idx = tid; idx < kTileM * 84; idx += kGemmThreads) {
@@ -945,9 +950,15 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             }
             if (MODE == 2) gemm_bar();   // X (z6 / its tangent) is reloaded by the next pass
             }  // passes
-            if (MODE == 1 && p.act_masks != nullptr && st == 0) {   // hand the derivative masks to the tangent launch
-                uint4* dst = reinterpret_cast<uint4*>(p.act_masks + (size_t)tile * (4 * kMaskStride));
-                for (int i = tid; i < 4 * kMaskStride / 16; i += kGemmThreads) dst[i] = reinterpret_cast<const uint4*>(mask)[i];
+            if (MODE == 1 && p.act_masks != nullptr && st == 0) {   // hand the activation derivatives to the tangent launch
+                if (p.df_act == ACT_SOFTPLUS) {   // fp32 derivatives: L2-resident per-CTA scratch -> per-tile buffer, streaming stores
+                    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.act_masks) + (size_t)tile * kUnits * 32);
+                    const float4* src = reinterpret_cast<const float4*>(c.dscr);
+                    for (int i = tid; i < kUnits * 32 / 4; i += kGemmThreads) __stcs(dst + i, src[i]);
+                } else {
+                    uint4* dst = reinterpret_cast<uint4*>(p.act_masks + (size_t)tile * (4 * kMaskStride));
+                    for (int i = tid; i < 4 * kMaskStride / 16; i += kGemmThreads) dst[i] = reinterpret_cast<const uint4*>(mask)[i];
+                }
             }
             if (!kGrad) {
                 gemm_bar();

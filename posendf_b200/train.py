@@ -45,7 +45,6 @@ A_END = 5376
 G0_ROW = 5376
 CHUNK = 65536      # poses per export launch (one dump buffer = 1.4 GB at this size)
 ENC_FLOATS = 3516
-MASK_BYTES_PER_TILE = 4 * 2656   # == pndf_act_mask_bytes(32)
 # explicit split-K factors of the weight-gradient GEMMs (tools/tune_wgrad.py on a B200, K = 32 768 poses): the outputs are
 # only 2 .. 32 tiles of 128x128, far fewer than 148 SMs
 _SPLIT_K = {0: 64, 1: 16, 2: 8, 3: 8, 4: 16, 5: 64}
@@ -63,8 +62,12 @@ class _Exports:
         T = (B + 31) // 32
         self.B, self.x, self.normalise = B, x, normalise
         self.dump = torch.empty(T * 32, DUMP_ROWS, device=x.device, dtype=torch.float32)
-        # activation-derivative bit masks of this launch: lets the tangent launch skip its primal pass (relu / lrelu)
-        self.masks = torch.empty(T * MASK_BYTES_PER_TILE, device=x.device, dtype=torch.uint8) if want_masks else None
+        # activation derivatives of this launch (bit masks, fp32 for softplus): the tangent launch then skips its primal pass
+        self.masks = None
+        if want_masks:
+            n = C.c_size_t()
+            _lib.check(eng.lib.pndf_act_handoff_bytes(eng._h, B, C.byref(n)))
+            self.masks = torch.empty(n.value, device=x.device, dtype=torch.uint8)
         self.dist = torch.empty(B, 1, device=x.device, dtype=torch.float32)
         self.grad = torch.empty(B, 21, 4, device=x.device, dtype=torch.float32)
         _lib.check(eng.lib.pndf_forward_grad_export(eng._h, x.data_ptr(), B, int(normalise), self.dist.data_ptr(),
@@ -96,12 +99,6 @@ def _out_act_deriv(d, act, beta):
         return sig, beta * sig * (1.0 - sig)
     pos = (d > 0).to(d.dtype)
     return pos, None
-
-
-def _hidden_act_deriv(z_next, beta):
-    """softplus: phi'(pre_l) and phi''(pre_l)/phi'(pre_l) recovered from z_{l+1} = phi(pre_l)."""
-    sig = -torch.expm1(-beta * z_next)               # phi' = sigma(beta pre) = 1 - exp(-beta z), accurate for tiny z
-    return sig, beta * (1.0 - sig)
 
 
 def _encoder_param_grads(eng, x, v, normalise, up1, upt, upz):
@@ -202,10 +199,15 @@ def _accumulate(out, net, eng, ex, up, w_eik):
             out.W(6).add_(pbar.t() @ Z[6])
             out.b(6).add_(pbar.sum().reshape(1))
             zbar = pbar @ W[6]                                                     # (B,64) adjoint of z_6
+            wdev = w_eik.reshape(1).contiguous()
             for l in range(5, -1, -1):
-                d1, ratio = _hidden_act_deriv(Z[l + 1], beta)                      # phi'(pre_l), phi''/phi'
-                pdot = Zd[l] / d1.clamp_min(1e-30)                                 # tangent of pre_l
-                pbar = zbar * d1 + (w_eik * ratio) * ex.cols(*A_ROWS[l]) * pdot    # A[l] = gbar_{l+1} * phi'
+                # pbar_l = zbar_{l+1} phi' + w_eik phi''/phi' a_l pdot_l , one fused element-wise pass (csrc/pndf_train_ops.cuh)
+                zbar = zbar.contiguous()
+                n = A_ROWS[l][1]
+                pbar = torch.empty(B, n, device=zbar.device, dtype=torch.float32)
+                _lib.check(eng.lib.pndf_softplus_adjoint(zbar.device.index, Z[l + 1].data_ptr(), Zd[l].data_ptr(),
+                                                         ex.cols(*A_ROWS[l]).data_ptr(), DUMP_ROWS, zbar.data_ptr(),
+                                                         wdev.data_ptr(), float(beta), B, n, pbar.data_ptr(), _stream(zbar)))
                 _wgrad(out.W(l), pbar, Z[l], _SPLIT_K[l])
                 out.b(l).add_(pbar.sum(0))
                 zbar = pbar @ W[l]

@@ -160,11 +160,13 @@ def test_device_weight_repack_equals_host_upload_and_follows_optimizer_steps():
     assert torch.equal(d1, c.forward(x)) and not torch.equal(d0, d1)
 
 
-def test_tangent_launch_with_mask_handoff_equals_two_pass_tangent():
-    """pndf_forward_tangent_export given launch 1's bit masks (skips its primal pass) == the self-contained two-pass launch"""
+@pytest.mark.parametrize("act", ["lrelu", "softplus"])
+def test_tangent_launch_with_mask_handoff_equals_two_pass_tangent(act):
+    """pndf_forward_tangent_export given launch 1's activation derivatives (bit masks / fp32 for softplus; skips its
+    primal pass) == the self-contained two-pass launch"""
     from posendf_b200 import _lib, train
     from posendf_b200.engine import Engine
-    eng = Engine(device=0, enc_act="lrelu", df_act="lrelu")
+    eng = Engine(device=0, enc_act=act, df_act=act)
     eng.set_weights_flat(synth.flatten_params(synth.make_params(4)))
     B = 200
     x = torch.from_numpy(synth.make_poses(4, B, kind="noisy", sigma=0.25)).cuda()
