@@ -16,3 +16,32 @@ for act in ("lrelu", "softplus"):
     torch.cuda.synchronize()
     print(act, float(d.mean()), float(g.abs().mean()), float((y - x).abs().max()), float(ga.abs().mean()))
 print("done")
+
+# training step (exports, derivative handoff, tangent launch, encoder gradient kernels, softplus adjoint, device repack),
+# host-buffer projection, denoise loop and rerank on ragged sizes
+import numpy as np
+from posendf_b200 import PoseNDF
+from posendf_b200.engine import knn_rerank
+for act in ("lrelu", "softplus"):
+    opt = {"train": {"device": "cuda", "loss_type": "l1", "batch_size": 4},
+           "model": {"StrEnc": {"use": True, "act": act, "beta": 100}, "DFNet": {"in_dim": 126, "dims": [256, 512, 1024, 512, 256, 64], "act": act, "beta": 100}}}
+    net = PoseNDF(opt)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_params(2).items()})
+    optim = torch.optim.Adam(net.parameters(), lr=1e-5)
+    B = 32 * 3 + 5
+    tp = torch.from_numpy(synth.make_poses(5, B, kind="noisy", sigma=0.25)); tm = torch.from_numpy(synth.make_poses(6, B + 9))
+    tgt = torch.from_numpy((synth.uniform01(7, B) * 0.5).astype(np.float32))
+    for _ in range(2):
+        optim.zero_grad()
+        _, ld = net(tp, tgt, tm, train=True, eikonal=1.0)
+        sum(ld.values()).backward()
+        optim.step()
+    xh, dh = net.project_host(torch.from_numpy(synth.make_poses(8, 1000)), steps=2)
+    aa, dd, _ = net.denoise_prior(torch.from_numpy(synth.make_axis_angle(9, 3 * 11)).reshape(3, 11, 21, 3), iterations=1, steps_per_iter=2)
+    torch.cuda.synchronize()
+    print(act, "train", {k: float(v.detach()) for k, v in ld.items()}, float(xh.abs().mean()), float(dd.mean()))
+db = torch.from_numpy(synth.make_poses(10, 500)).cuda()
+q = torch.from_numpy(synth.make_poses(11, 37)).cuda()
+cand = torch.randint(0, 500, (37, 50), device="cuda", dtype=torch.int32)
+print("rerank", [t.shape for t in knn_rerank(q, db, cand)])
+print("done-train")
