@@ -292,7 +292,7 @@ def main():
                        "l2": "256 MiB flush write between timed steps", "parallelism": f"pose-sharded x{world}"
                        + (", NCCL all-gather of projected poses per step" if world > 1 else "")},
             "roofline": {"bound": "fp32_fma", "achieved": ach_tf, "peak": p_fp32, "unit": "TFLOP/s", "frac": ach_tf / p_fp32,
-                         "traffic": traffic, "kernel": "pndf_fused_kernel<true>", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "kernel": "pndf_fused_kernel<1>", "kernel_ms": kernel_ms,
                          "peak_source": "in-process FFMA micro-benchmark (pndf_fp32_peak: scalar %.1f, packed f32x2 %.1f TFLOP/s); "
                                         "tensor cores unused: fp32 parity bar 1e-5" % (p_ffma, p_ffma2),
                          "algorithmic_flops_per_pose": FLOPS_PER_PROJECTION},

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpndf.so")
+LIB_PATH = os.environ.get("PNDF_LIBRARY") or os.path.join(_HERE, "libpndf.so")      # PNDF_LIBRARY: A/B builds (tools/)
 
 ACT = {"relu": 0, "lrelu": 1, "softplus": 2}
 MAX_HIDDEN = 8

@@ -525,6 +525,9 @@ __device__ __forceinline__ void dump_rows(float* dbg, int row0, const float* buf
 
 // ------------------------------------------------------------------------------------------------ encoder
 __constant__ int c_parent[21] = {-1, -1, -1, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19};
+// non-root joint pairs of the encoder schedule (two independent sub-trees per step), after (1,0) and (3,2)
+__constant__ int c_pair_a[7] = {5, 7, 9, 12, 14, 16, 17};
+__constant__ int c_pair_b[7] = {4, 6, 8, 10, 11, 13, 15};
 
 __device__ __forceinline__ int enc_off(int i) { return (i < 3) ? i * 116 : 348 + (i - 3) * 176; }
 
@@ -615,16 +618,12 @@ __device__ __forceinline__ void encoder_forward(const float* encw, const float* 
                                                 float apar) {
     enc_fwd_pair<SOFT, true, true>(encw, qs, feat, stash, e, apar, 1, 0);
     enc_fwd_pair<SOFT, false, true>(encw, qs, feat, stash, e, apar, 3, 2);
-    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 5, 4);
-    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 7, 6);
-    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 9, 8);
-    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 12, 10);
-    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 14, 11);
-    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 16, 13);
-    enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, 17, 15);
-    enc_fwd_one<SOFT>(encw, qs, feat, stash, e, apar, 18);
-    enc_fwd_one<SOFT>(encw, qs, feat, stash, e, apar, 19);
-    enc_fwd_one<SOFT>(encw, qs, feat, stash, e, apar, 20);
+    // one copy of the pair body, walked 7 times (fully unrolled the encoder was 20 000 SASS instructions and stalled on
+    // instruction fetch for a third of its cycles)
+#pragma unroll 1
+    for (int s = 0; s < 7; ++s) enc_fwd_pair<SOFT, false, false>(encw, qs, feat, stash, e, apar, c_pair_a[s], c_pair_b[s]);
+#pragma unroll 1
+    for (int i = 18; i <= 20; ++i) enc_fwd_one<SOFT>(encw, qs, feat, stash, e, apar, i);
 }
 
 // reverse step of one joint: everything up to (not including) the writes.  ua/ub = this lane's gradient w.r.t. its input
@@ -693,19 +692,15 @@ __device__ __forceinline__ void enc_bwd_pair(const float* encw, const float* qs,
 template <bool SOFT>
 __device__ __forceinline__ void encoder_backward(const float* encw, const float* qs, const float* feat, float* gbuf,
                                                  const EncLane& e, float apar) {
+#pragma unroll 1
     for (int i = 20; i >= 18; --i) {
         float ua, ub;
         bone_backward<SOFT, false>(encw, qs, feat, gbuf, i, e, apar, ua, ub);
         bone_backward_write<false>(gbuf, i, e, ua, ub);
         __syncwarp();
     }
-    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 17, 15);
-    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 16, 13);
-    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 14, 11);
-    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 12, 10);
-    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 9, 8);
-    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 7, 6);
-    enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, 5, 4);
+#pragma unroll 1
+    for (int s = 6; s >= 0; --s) enc_bwd_pair<SOFT, false, false>(encw, qs, feat, gbuf, e, apar, c_pair_a[s], c_pair_b[s]);
     enc_bwd_pair<SOFT, false, true>(encw, qs, feat, gbuf, e, apar, 3, 2);
     enc_bwd_pair<SOFT, true, true>(encw, qs, feat, gbuf, e, apar, 1, 0);
 }
