@@ -167,6 +167,15 @@ int pndf_encoder_param_grads(pndf_handle* h, const float* pose_dev, const float*
 int pndf_knn_rerank(int device, const float* query_dev, int64_t Q, const float* database_dev, const int32_t* cand_dev, int K,
                     int metric, int weighted, float* out_val_dev, int32_t* out_pos_dev, void* stream);
 
+/* The same labels WITHOUT a candidate stage: exact 5 nearest database poses of every query over the whole database
+ * (what data/prepare_traindata.py:138-170 approximates with 500 faiss candidates before its rerank; identical to
+ * pndf_knn_rerank whenever the candidate list contains the true neighbours).  out_idx_dev: Q*5 int32 row indices into
+ * the database (N <= 2^31-1), ascending distance, ties by lower index.  Brute force on the fp32 pipe: 105 FMA per
+ * (query, database pose) pair, database tiles streamed once per 64 queries through shared memory by TMA bulk copies.
+ * database_dev must be 16-byte aligned.  Stateless; scratch comes from the stream-ordered allocator. */
+int pndf_knn_exact(int device, const float* query_dev, int64_t Q, const float* database_dev, int64_t N, int metric, int weighted,
+                   float* out_val_dev, int32_t* out_idx_dev, void* stream);
+
 /* Measurement helpers used by bench.py (not on the data path):
  *   pndf_fp32_peak: in-process FFMA micro-benchmark, dense fp32 FMA TFLOP/s of this GPU right now.
  *     variant 0 = scalar FFMA, 1 / 5 = packed FFMA2 (fma.rn.f32x2) with the pose scalar / the feature pair as the

@@ -312,3 +312,19 @@ def knn_rerank(query, database, cand_idx, metric="geo", weighted=False, k=5):
     dis = np.sum(w * per_joint, axis=2) if weighted else np.mean(per_joint, axis=2)
     order = np.argsort(dis, axis=1, kind="stable")[:, :k]
     return np.take_along_axis(dis, order, axis=1), order
+
+
+def knn_exact(query, database, metric="geo", weighted=False, k=5, chunk=64):
+    """The reference's dist_calc (data/dist_utils.py:19-50) with the WHOLE database as the candidate list of every
+    query: exact k nearest database poses (values (Q,k) ascending, database row indices (Q,k); ties by lower index).
+    What data/prepare_traindata.py:138-170 approximates through its faiss candidate stage."""
+    q = np.asarray(query)
+    n = len(database)
+    vals, idxs = [], []
+    for c0 in range(0, len(q), chunk):
+        qq = q[c0:c0 + chunk]
+        cand = np.broadcast_to(np.arange(n), (len(qq), n))
+        v, p = knn_rerank(qq, database, cand, metric, weighted, k)
+        vals.append(v)
+        idxs.append(p)
+    return np.concatenate(vals), np.concatenate(idxs)

@@ -43,6 +43,7 @@ SYMBOLS = {
     "pndf_encoder_tangent": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "pndf_encoder_param_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pndf_knn_rerank": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pndf_knn_exact": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pndf_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pndf_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "pndf_num_sms": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),

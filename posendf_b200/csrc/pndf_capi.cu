@@ -571,6 +571,49 @@ int pndf_knn_rerank(int device, const float* query_dev, int64_t Q, const float* 
     return 0;
 }
 
+int pndf_knn_exact(int device, const float* query_dev, int64_t Q, const float* database_dev, int64_t N, int metric, int weighted,
+                   float* out_val_dev, int32_t* out_idx_dev, void* stream) {
+    if (Q == 0) return 0;
+    if (Q < 0 || N < kKnnK || N > 0x7fffffffLL || !query_dev || !database_dev || !out_val_dev || !out_idx_dev)
+        return fail("pndf_knn_exact: null argument or fewer than 5 database poses");
+    if (metric != 0 && metric != 1) return fail("pndf_knn_exact: metric must be 0 (geo) or 1 (euc)");
+    if ((reinterpret_cast<uintptr_t>(database_dev) & 15) != 0) return fail("pndf_knn_exact: database must be 16-byte aligned");
+    CUDA_OK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    static bool attr_set[64] = {};
+    if (device < 64 && !attr_set[device]) {
+        CUDA_OK(cudaFuncSetAttribute(knn_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExSmem));
+        CUDA_OK(cudaFuncSetAttribute(knn_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExSmem));
+        attr_set[device] = true;
+    }
+    int sms = 148;
+    CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    // database slices: enough CTAs for ~4 per SM, slices are whole 128-row tiles
+    const long long gx = (Q + kExQ - 1) / kExQ;
+    const long long tiles = (N + kExD - 1) / kExD;
+    long long want = std::max<long long>(1, (4LL * sms + gx - 1) / gx);
+    want = std::min(want, tiles);
+    const long long tiles_per_split = (tiles + want - 1) / want;
+    const int nsplit = (int)((tiles + tiles_per_split - 1) / tiles_per_split);
+    float* part_val = nullptr;
+    int32_t* part_idx = nullptr;
+    const size_t nelem = (size_t)Q * nsplit * kKnnK;
+    CUDA_OK(cudaMallocAsync(&part_val, nelem * sizeof(float), st));
+    CUDA_OK(cudaMallocAsync(&part_idx, nelem * sizeof(int32_t), st));
+    KnnExactParams p{};
+    p.query = query_dev; p.database = database_dev; p.part_val = part_val; p.part_idx = part_idx;
+    p.Q = Q; p.N = N; p.rows_per_split = tiles_per_split * kExD; p.nsplit = nsplit; p.weighted = weighted;
+    const dim3 grid((unsigned)gx, (unsigned)nsplit);
+    if (metric == 0) knn_exact_kernel<0><<<grid, kExThreads, kExSmem, st>>>(p);
+    else knn_exact_kernel<1><<<grid, kExThreads, kExSmem, st>>>(p);
+    CUDA_OK(cudaGetLastError());
+    knn_merge_kernel<<<(unsigned)((Q + 127) / 128), 128, 0, st>>>(part_val, part_idx, Q, nsplit, out_val_dev, out_idx_dev);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaFreeAsync(part_val, st));
+    CUDA_OK(cudaFreeAsync(part_idx, st));
+    return 0;
+}
+
 int pndf_launch_count(pndf_handle* h, int64_t* n) {
     if (!h || !n) return fail("null argument");
     *n = h->launches;

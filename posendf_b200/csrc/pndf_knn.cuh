@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pndf_kernel.cuh"
+
 namespace pndf {
 
 constexpr int kKnnK = 5;
@@ -84,6 +86,178 @@ __global__ void __launch_bounds__(128) knn_rerank_kernel(const KnnParams p) {
         p.out_val[q * kKnnK + lane] = ov;
         p.out_pos[q * kKnnK + lane] = op;
     }
+}
+
+// ------------------------------------------------------------------------------------------------ exact search
+// Exact k = 5 nearest database poses of every query under the same metrics -- the labels data/prepare_traindata.py:138-170
+// approximates with a faiss candidate list (500 nearest by SMPL joint positions) before its rerank.  Brute force is
+// fp32-FMA-bound, not HBM-bound: every database row staged in shared memory is scored against 64 queries.
+//
+//   grid  (ceil(Q/64), nsplit): a CTA owns 64 queries and one contiguous slice of the database
+//   CTA   256 threads = 16 query groups x 16 row groups; a thread scores 4 queries x 8 rows per 128-row tile
+//         (rows td, td+16, ...: consecutive lanes read consecutive 336-byte rows, conflict-free LDS.128)
+//   tiles 128 rows = 43 008 contiguous bytes, TMA bulk copy into a 2-stage shared-memory ring (mbarrier complete_tx)
+//   top-5 per thread and query in registers, merged over the 16 row groups in shared memory, then over the database
+//         slices by knn_merge_kernel.  Ties: lower database index first.
+constexpr int kExQ = 64, kExD = 128, kExThreads = 256;
+constexpr int kExSmem = kExQ * 84 * 4 + 2 * kExD * 84 * 4 + 2 * 8 + 16;
+
+struct KnnExactParams {
+    const float* query;      // Q x 84
+    const float* database;   // N x 84
+    float* part_val;         // Q x nsplit x 5
+    int32_t* part_idx;
+    long long Q, N, rows_per_split;
+    int nsplit, weighted;
+};
+
+__device__ __forceinline__ void top5_insert(float (&bv)[kKnnK], int (&bi)[kKnnK], float d, int idx) {
+    bv[kKnnK - 1] = d; bi[kKnnK - 1] = idx;
+#pragma unroll
+    for (int i = kKnnK - 1; i > 0; --i) {
+        const bool sw = (bv[i] < bv[i - 1]) || (bv[i] == bv[i - 1] && bi[i] < bi[i - 1]);
+        if (sw) {
+            const float tv = bv[i]; bv[i] = bv[i - 1]; bv[i - 1] = tv;
+            const int ti = bi[i]; bi[i] = bi[i - 1]; bi[i - 1] = ti;
+        }
+    }
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(kExThreads, 2) knn_exact_kernel(const KnnExactParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* qs = reinterpret_cast<float*>(smem);
+    float* dbs = qs + kExQ * 84;
+    uint64_t* full = reinterpret_cast<uint64_t*>(dbs + 2 * kExD * 84);
+    const int tid = threadIdx.x, tq = tid >> 4, td = tid & 15;
+    const long long q0 = (long long)blockIdx.x * kExQ;
+    const long long s0 = (long long)blockIdx.y * p.rows_per_split;
+    const long long s1 = min(p.N, s0 + p.rows_per_split);
+    const int ntiles = (int)((s1 - s0 + kExD - 1) / kExD);
+    const uint32_t bar_s = smem_u32(full), dbs_s = smem_u32(dbs);
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int idx = tid; idx < kExQ * 84; idx += kExThreads) {
+        const long long q = q0 + idx / 84;
+        qs[idx] = (q < p.Q) ? __ldg(p.query + q0 * 84 + idx) : 0.0f;
+    }
+    __syncthreads();
+    auto issue = [&](int t) {     // thread 0: bulk copy of tile t into stage t & 1
+        const long long r0 = s0 + (long long)t * kExD;
+        const uint32_t bytes = (uint32_t)(min((long long)kExD, s1 - r0) * 336);
+        const uint32_t bar = bar_s + (t & 1) * 8;
+        mbar_expect_tx_s(bar, bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         dbs_s + (t & 1) * (kExD * 336)),
+                     "l"(p.database + r0 * 84), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
+    if (tid == 0) {
+        if (ntiles > 0) issue(0);
+        if (ntiles > 1) issue(1);
+    }
+    float wsum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 21; ++j) wsum += p.weighted ? c_joint_w[j] : (1.0f / 21.0f);
+
+    float bv[4][kKnnK];
+    int bi[4][kKnnK];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < kKnnK; ++k) { bv[i][k] = 3.0e38f; bi[i][k] = 0x7fffffff; }
+
+    for (int t = 0; t < ntiles; ++t) {
+        mbar_wait_s(bar_s + (t & 1) * 8, (uint32_t)((t >> 1) & 1));
+        const float* tile = dbs + (t & 1) * (kExD * 84);
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int r = 0; r < 8; ++r) acc[i][r] = 0.0f;
+#pragma unroll 3
+        for (int j = 0; j < 21; ++j) {
+            const float w = p.weighted ? c_joint_w[j] : (1.0f / 21.0f);
+            float4 qv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(qs + (tq * 4 + i) * 84 + j * 4);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 d = *reinterpret_cast<const float4*>(tile + (td + 16 * r) * 84 + j * 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (METRIC == 0) {
+                        const float dot = fmaf(qv[i].w, d.w, fmaf(qv[i].z, d.z, fmaf(qv[i].y, d.y, qv[i].x * d.x)));
+                        acc[i][r] = fmaf(w, fabsf(dot), acc[i][r]);
+                    } else {
+                        const float a = qv[i].x - d.x, b = qv[i].y - d.y, c = qv[i].z - d.z, e = qv[i].w - d.w;
+                        acc[i][r] = fmaf(w, sqrtf(fmaf(e, e, fmaf(c, c, fmaf(b, b, a * a)))), acc[i][r]);
+                    }
+                }
+            }
+        }
+        const long long row_base = s0 + (long long)t * kExD + td;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const long long row = row_base + 16 * r;
+            if (row < s1) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float dist = (METRIC == 0) ? (wsum - acc[i][r]) : acc[i][r];
+                    if (dist < bv[i][kKnnK - 1]) top5_insert(bv[i], bi[i], dist, (int)row);
+                }
+            }
+        }
+        __syncthreads();                              // everyone is done with stage t & 1
+        if (tid == 0 && t + 2 < ntiles) issue(t + 2);
+    }
+    // ---- merge the 16 row groups of every query (stage 0 of the ring is free now)
+    float* mv = dbs;
+    int* mi = reinterpret_cast<int*>(dbs + kExQ * 16 * kKnnK);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < kKnnK; ++k) {
+            mv[((tq * 4 + i) * 16 + td) * kKnnK + k] = bv[i][k];
+            mi[((tq * 4 + i) * 16 + td) * kKnnK + k] = bi[i][k];
+        }
+    __syncthreads();
+    if (tid < kExQ && q0 + tid < p.Q) {
+        float fv[kKnnK];
+        int fi[kKnnK];
+#pragma unroll
+        for (int k = 0; k < kKnnK; ++k) { fv[k] = 3.0e38f; fi[k] = 0x7fffffff; }
+        for (int c = 0; c < 16 * kKnnK; ++c) {
+            const float d = mv[tid * 16 * kKnnK + c];
+            const int ix = mi[tid * 16 * kKnnK + c];
+            if (d < fv[kKnnK - 1] || (d == fv[kKnnK - 1] && ix < fi[kKnnK - 1])) top5_insert(fv, fi, d, ix);
+        }
+        const long long o = ((q0 + tid) * p.nsplit + blockIdx.y) * kKnnK;
+#pragma unroll
+        for (int k = 0; k < kKnnK; ++k) { p.part_val[o + k] = fv[k]; p.part_idx[o + k] = fi[k]; }
+    }
+}
+
+// one thread per query: top-5 of the nsplit x 5 partial results
+__global__ void knn_merge_kernel(const float* part_val, const int32_t* part_idx, long long Q, int nsplit, float* out_val,
+                                 int32_t* out_idx) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    float fv[kKnnK];
+    int fi[kKnnK];
+#pragma unroll
+    for (int k = 0; k < kKnnK; ++k) { fv[k] = 3.0e38f; fi[k] = 0x7fffffff; }
+    for (int c = 0; c < nsplit * kKnnK; ++c) {
+        const float d = part_val[q * nsplit * kKnnK + c];
+        const int ix = part_idx[q * nsplit * kKnnK + c];
+        if (d < fv[kKnnK - 1] || (d == fv[kKnnK - 1] && ix < fi[kKnnK - 1])) top5_insert(fv, fi, d, ix);
+    }
+#pragma unroll
+    for (int k = 0; k < kKnnK; ++k) { out_val[q * kKnnK + k] = fv[k]; out_idx[q * kKnnK + k] = fi[k]; }
 }
 
 }  // namespace pndf

@@ -170,3 +170,20 @@ def knn_rerank(query, database, cand_idx, metric="geo", weighted=False):
     _lib.check(lib.pndf_knn_rerank(q.device.index or 0, q.data_ptr(), Q, db.data_ptr(), ci.data_ptr(), K,
                                    {"geo": 0, "euc": 1}[metric], int(weighted), val.data_ptr(), pos.data_ptr(), _stream_ptr(q.device)))
     return val, pos
+
+
+def knn_exact(query, database, metric="geo", weighted=False):
+    """exact 5 nearest database poses of every query under the reference's `geo` / `euc` metric (data/dist_utils.py:19-50)
+    over the WHOLE database -- the labels data/prepare_traindata.py:138-170 approximates through faiss candidates.
+    CUDA tensors query (Q,21,4), database (N,21,4) fp32 -> (distances (Q,5) ascending, database row indices (Q,5) int32)."""
+    lib = _lib.load()
+    q = query.detach().to(torch.float32).reshape(-1, 84).contiguous()
+    db = database.detach().to(torch.float32).reshape(-1, 84).contiguous()
+    if not (q.is_cuda and db.is_cuda):
+        raise RuntimeError("knn_exact needs CUDA tensors (there is no CPU fallback)")
+    Q, N = q.shape[0], db.shape[0]
+    val = torch.empty(Q, 5, device=q.device, dtype=torch.float32)
+    idx = torch.empty(Q, 5, device=q.device, dtype=torch.int32)
+    _lib.check(lib.pndf_knn_exact(q.device.index or 0, q.data_ptr(), Q, db.data_ptr(), N, {"geo": 0, "euc": 1}[metric],
+                                  int(weighted), val.data_ptr(), idx.data_ptr(), _stream_ptr(q.device)))
+    return val, idx

@@ -29,5 +29,16 @@ for name in ("geo", "euc"):
             val, ind = calc.dist_calc(torch.from_numpy(qr).to(dt), torch.from_numpy(db[idx]).to(dt), K, 5)
             out[f"{name}_{int(weighted)}_val{tag}"] = val.numpy()
             out[f"{name}_{int(weighted)}_idx{tag}"] = ind.numpy()
+# exact search = the same reference classes with the whole (small) database as every query's candidate list
+NEX, QEX = 1500, 24
+out["NEX"], out["QEX"] = NEX, QEX
+full = np.broadcast_to(db[:NEX], (QEX, NEX, 21, 4))
+for name in ("geo", "euc"):
+    for weighted in (False, True):
+        calc = ns[name](QEX, device="cpu", weighted=weighted)
+        calc.joint_weights = calc.joint_weights.to(torch.float64)
+        val, ind = calc.dist_calc(torch.from_numpy(qr[:QEX]).double(), torch.from_numpy(np.ascontiguousarray(full)).double(), NEX, 5)
+        out[f"exact_{name}_{int(weighted)}_val64"] = val.numpy()
+        out[f"exact_{name}_{int(weighted)}_idx64"] = ind.numpy()
 np.savez_compressed(os.path.join(HERE, "knn_rerank.npz"), **out)
 print({k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items() if "64" in str(k) or k in ("Q", "K")})

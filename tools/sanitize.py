@@ -44,4 +44,6 @@ db = torch.from_numpy(synth.make_poses(10, 500)).cuda()
 q = torch.from_numpy(synth.make_poses(11, 37)).cuda()
 cand = torch.randint(0, 500, (37, 50), device="cuda", dtype=torch.int32)
 print("rerank", [t.shape for t in knn_rerank(q, db, cand)])
+from posendf_b200.engine import knn_exact
+print("exact", [t.shape for t in knn_exact(q, db, "geo")], [t.shape for t in knn_exact(q[:3], db[:133], "euc", True)])
 print("done-train")
