@@ -26,7 +26,6 @@ as the cross-check the tests compare the fused step with, not as a fallback.
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 import torch.nn as nn
 

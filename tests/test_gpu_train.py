@@ -164,7 +164,7 @@ def test_device_weight_repack_equals_host_upload_and_follows_optimizer_steps():
 def test_tangent_launch_with_mask_handoff_equals_two_pass_tangent(act):
     """pndf_forward_tangent_export given launch 1's activation derivatives (bit masks / fp32 for softplus; skips its
     primal pass) == the self-contained two-pass launch"""
-    from posendf_b200 import _lib, train
+    from posendf_b200 import train
     from posendf_b200.engine import Engine
     eng = Engine(device=0, enc_act=act, df_act=act)
     eng.set_weights_flat(synth.flatten_params(synth.make_params(4)))

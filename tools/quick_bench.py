@@ -1,5 +1,5 @@
 """Quick timing of the fused kernel (not the contract bench): poses/s for fwd, fwd+grad+step."""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from posendf_b200 import synth
