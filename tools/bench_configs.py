@@ -2,7 +2,7 @@
   C3: 50-step projection loop, 131 072 poses (1 048 576 / 8)          -> poses/s and pose-steps/s
   C4: motion denoise prior loop, 128 sequences x 300 frames (512x300 / 4), 100 Adam steps
 """
-import json, os, sys, time
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from posendf_b200 import synth
