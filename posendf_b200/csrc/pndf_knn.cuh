@@ -195,7 +195,11 @@ __global__ void __launch_bounds__(kExThreads, 2) knn_exact_kernel(const KnnExact
                         acc[i][r] = fmaf(w, fabsf(dot), acc[i][r]);
                     } else {
                         const float a = qv[i].x - d.x, b = qv[i].y - d.y, c = qv[i].z - d.z, e = qv[i].w - d.w;
-                        acc[i][r] = fmaf(w, sqrtf(fmaf(e, e, fmaf(c, c, fmaf(b, b, a * a)))), acc[i][r]);
+                        // |q - q'| = s * rsqrt(s): one MUFU + one FMUL instead of the IEEE sqrt sequence (2-3 ulp, far inside
+                        // the 1e-5 label tolerance); rsqrt(0) = inf is masked
+                        const float s2 = fmaf(e, e, fmaf(c, c, fmaf(b, b, a * a)));
+                        const float nrm = (s2 > 0.0f) ? s2 * rsqrtf(s2) : 0.0f;
+                        acc[i][r] = fmaf(w, nrm, acc[i][r]);
                     }
                 }
             }
