@@ -158,6 +158,13 @@ int pndf_encoder_param_grads(pndf_handle* h, const float* pose_dev, const float*
                              const float* up_first_dev, const float* up_tangent_dev, const float* up_second_dev,
                              float* grads_dev, void* stream);
 
+/* Rotation formats on either side of the path: pytorch3d.transforms.axis_angle_to_quaternion / quaternion_to_axis_angle
+ * (0.7.2; experiments/sample_poses.py:60,80, experiments/motion_denoise.py:81, model/load_data.py:108) on n rotations
+ * (n = poses * 21): aa n*3 floats, quat n*4 floats (real part first, 16-byte aligned).  Formulas restated from the
+ * published source -- parity unpinned, pytorch3d is not vendored in the reference.  Stateless. */
+int pndf_axis_angle_to_quaternion(int device, const float* aa_dev, int64_t n, float* quat_dev, void* stream);
+int pndf_quaternion_to_axis_angle(int device, const float* quat_dev, int64_t n, float* aa_dev, void* stream);
+
 /* Distance-label rerank of the dataset preparation (data/dist_utils.py:19-30 `euc`, :41-50 `geo`, topk at
  * data/prepare_traindata.py:156): for each of Q query poses (Q*84 floats) the 5 nearest of its K candidates, given as
  * int32 indices (Q*K) into a database of unit-quaternion poses (N*84 floats).  metric 0 = geo: mean_j (1 - |<q_j, q'_j>|),

@@ -328,3 +328,18 @@ def knn_exact(query, database, metric="geo", weighted=False, k=5, chunk=64):
         vals.append(v)
         idxs.append(p)
     return np.concatenate(vals), np.concatenate(idxs)
+
+
+def quaternion_to_axis_angle(quat):
+    """pytorch3d 0.7.2 transforms.quaternion_to_axis_angle (not vendored in /root/reference; formula as published):
+    norms = |q[1:]|, half = atan2(norms, q[0]), angle = 2 half, aa = q[1:] / (sin(half)/angle), small-angle
+    (|angle| < 1e-6) denominator 1/2 - angle^2/48.  PARITY UNPINNED (no copy of pytorch3d here)."""
+    q = np.asarray(quat)
+    dt = q.dtype
+    nrm = np.sqrt(np.sum(q[..., 1:] * q[..., 1:], axis=-1, keepdims=True))
+    half = np.arctan2(nrm, q[..., :1])
+    ang = dt.type(2) * half
+    small = np.abs(ang) < 1e-6
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(small, dt.type(0.5) - ang * ang / dt.type(48), np.sin(half) / np.where(small, dt.type(1), ang))
+    return q[..., 1:] / k

@@ -556,6 +556,24 @@ int pndf_softplus_adjoint(int device, const float* z_next_dev, const float* zdot
     return 0;
 }
 
+int pndf_axis_angle_to_quaternion(int device, const float* aa_dev, int64_t n, float* quat_dev, void* stream) {
+    if (n == 0) return 0;
+    if (n < 0 || !aa_dev || !quat_dev) return fail("pndf_axis_angle_to_quaternion: bad argument");
+    CUDA_OK(cudaSetDevice(device));
+    aa_to_quat_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(aa_dev, quat_dev, n);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pndf_quaternion_to_axis_angle(int device, const float* quat_dev, int64_t n, float* aa_dev, void* stream) {
+    if (n == 0) return 0;
+    if (n < 0 || !aa_dev || !quat_dev) return fail("pndf_quaternion_to_axis_angle: bad argument");
+    CUDA_OK(cudaSetDevice(device));
+    quat_to_aa_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(quat_dev, aa_dev, n);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int pndf_knn_rerank(int device, const float* query_dev, int64_t Q, const float* database_dev, const int32_t* cand_dev, int K,
                     int metric, int weighted, float* out_val_dev, int32_t* out_pos_dev, void* stream) {
     if (Q == 0) return 0;

@@ -9,6 +9,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pndf_kernel.cuh"
+
 namespace pndf {
 
 struct SoftplusAdjParams {
@@ -45,6 +47,30 @@ __global__ void __launch_bounds__(256) softplus_adjoint_kernel(const SoftplusAdj
         }
         *reinterpret_cast<float4*>(p.pbar + b * p.n + j) = make_float4(o[0], o[1], o[2], o[3]);
     }
+}
+
+// ---- rotation-format conversions on either side of the path (pytorch3d 0.7.2 transforms, formulas restated; the callers
+// experiments/sample_poses.py:60,80 and experiments/motion_denoise.py:81 apply them around the projection / prior).
+// One thread per joint rotation; n = number of rotations (B * 21).
+__global__ void aa_to_quat_kernel(const float* __restrict__ aa, float* __restrict__ quat, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a[3] = {aa[i * 3], aa[i * 3 + 1], aa[i * 3 + 2]};
+    float q[4];
+    aa_to_quat(a, q);
+    *reinterpret_cast<float4*>(quat + i * 4) = make_float4(q[0], q[1], q[2], q[3]);
+}
+// quaternion_to_axis_angle: norms = |q[1:]|, half = atan2(norms, q[0]), angle = 2 half,
+// aa = q[1:] / (sin(half)/angle)   with the small-angle series 1/2 - angle^2/48 for |angle| < 1e-6
+__global__ void quat_to_aa_kernel(const float* __restrict__ quat, float* __restrict__ aa, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 q = *reinterpret_cast<const float4*>(quat + i * 4);
+    const float nrm = sqrtf(q.y * q.y + q.z * q.z + q.w * q.w);
+    const float half = atan2f(nrm, q.x);
+    const float ang = 2.0f * half;
+    const float k = (fabsf(ang) < 1e-6f) ? (0.5f - ang * ang / 48.0f) : (sinf(half) / ang);
+    aa[i * 3] = q.y / k; aa[i * 3 + 1] = q.z / k; aa[i * 3 + 2] = q.w / k;
 }
 
 }  // namespace pndf

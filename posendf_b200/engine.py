@@ -187,3 +187,25 @@ def knn_exact(query, database, metric="geo", weighted=False):
     _lib.check(lib.pndf_knn_exact(q.device.index or 0, q.data_ptr(), Q, db.data_ptr(), N, {"geo": 0, "euc": 1}[metric],
                                   int(weighted), val.data_ptr(), idx.data_ptr(), _stream_ptr(q.device)))
     return val, idx
+
+
+def axis_angle_to_quaternion(aa):
+    """pytorch3d.transforms.axis_angle_to_quaternion on a CUDA tensor (..., 3) -> (..., 4), real part first"""
+    lib = _lib.load()
+    a = aa.detach().to(torch.float32).contiguous()
+    if not a.is_cuda:
+        raise RuntimeError("axis_angle_to_quaternion needs a CUDA tensor (there is no CPU fallback)")
+    out = torch.empty(*a.shape[:-1], 4, device=a.device, dtype=torch.float32)
+    _lib.check(lib.pndf_axis_angle_to_quaternion(a.device.index or 0, a.data_ptr(), a.numel() // 3, out.data_ptr(), _stream_ptr(a.device)))
+    return out
+
+
+def quaternion_to_axis_angle(quat):
+    """pytorch3d.transforms.quaternion_to_axis_angle on a CUDA tensor (..., 4) -> (..., 3)"""
+    lib = _lib.load()
+    q = quat.detach().to(torch.float32).contiguous()
+    if not q.is_cuda:
+        raise RuntimeError("quaternion_to_axis_angle needs a CUDA tensor (there is no CPU fallback)")
+    out = torch.empty(*q.shape[:-1], 3, device=q.device, dtype=torch.float32)
+    _lib.check(lib.pndf_quaternion_to_axis_angle(q.device.index or 0, q.data_ptr(), q.numel() // 4, out.data_ptr(), _stream_ptr(q.device)))
+    return out
