@@ -59,3 +59,34 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libpndf.so"))
     with pytest.raises(RuntimeError, match="no CPU / PyTorch fallback"):
         _lib.load()
+
+
+def test_host_side_layout_constants_match_the_kernel_header():
+    """posendf_b200/train.py addresses the training exports by column: its constants must be the kernel's."""
+    import re
+    from posendf_b200 import train
+    src = open(os.path.join(ROOT, "posendf_b200", "csrc", "pndf_kernel.cuh")).read()
+
+    def const(name):
+        m = re.search(r"constexpr int %s\s*=\s*([0-9]+)" % name, src)
+        assert m, name
+        return int(m.group(1))
+
+    assert train.DUMP_ROWS == const("kDumpRows")
+    assert train.ENC_FLOATS == const("kEncFloats")
+    widths = [256, 512, 1024, 512, 256, 64]
+    assert sum(widths) == const("kUnits")
+    # layer inputs z_0..z_6 are contiguous from column 0, adjoints a_5..a_0 follow, then the z_0 adjoint
+    off = 0
+    for (c0, w), width in zip(train.Z_ROWS, [128] + widths):
+        assert c0 == off
+        assert w in (None, width)
+        off += width
+    assert off == train.Z_END
+    for l in (5, 4, 3, 2, 1, 0):
+        assert train.A_ROWS[l] == (off, widths[l])
+        off += widths[l]
+    assert off == train.A_END == train.G0_ROW and train.G0_ROW + 128 == train.DUMP_ROWS
+    # the dump offsets the kernel passes to dump_rows()
+    for c0 in [r[0] for r in train.Z_ROWS[1:]] + [r[0] for r in train.A_ROWS] + [train.G0_ROW]:
+        assert re.search(r"dump_rows\(dbg_[ps], %d(\s|,|\+)" % c0, src), c0
