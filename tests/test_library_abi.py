@@ -90,3 +90,23 @@ def test_host_side_layout_constants_match_the_kernel_header():
     # the dump offsets the kernel passes to dump_rows()
     for c0 in [r[0] for r in train.Z_ROWS[1:]] + [r[0] for r in train.A_ROWS] + [train.G0_ROW]:
         assert re.search(r"dump_rows\(dbg_[ps], %d(\s|,|\+)" % c0, src), c0
+
+
+def test_stateless_entry_points_reject_bad_arguments_before_touching_cuda():
+    import ctypes as C
+    from posendf_b200 import _lib
+    lib = _lib.load()
+    dummy = C.c_void_p(16)
+    # fewer than 5 database poses / null pointers / unknown metric
+    assert lib.pndf_knn_exact(0, dummy, 4, dummy, 3, 0, 0, dummy, dummy, None) != 0
+    assert b"pndf_knn_exact" in lib.pndf_last_error()
+    assert lib.pndf_knn_exact(0, None, 4, dummy, 100, 0, 0, dummy, dummy, None) != 0
+    assert lib.pndf_knn_exact(0, dummy, 4, dummy, 100, 7, 0, dummy, dummy, None) != 0
+    assert lib.pndf_knn_exact(0, dummy, 4, C.c_void_p(20), 100, 0, 0, dummy, dummy, None) != 0      # misaligned database
+    assert lib.pndf_knn_rerank(0, dummy, 4, dummy, dummy, 3, 0, 0, dummy, dummy, None) != 0          # K < 5
+    assert lib.pndf_softplus_adjoint(0, dummy, dummy, dummy, 5504, dummy, None, 100.0, 8, 6, dummy, None) != 0   # n % 4 != 0
+    assert lib.pndf_axis_angle_to_quaternion(0, None, 3, dummy, None) != 0
+    assert lib.pndf_quaternion_to_axis_angle(0, dummy, -1, dummy, None) != 0
+    # empty work is a no-op, not an error
+    assert lib.pndf_knn_exact(0, None, 0, None, 0, 0, 0, None, None, None) == 0
+    assert lib.pndf_axis_angle_to_quaternion(0, None, 0, None, None) == 0
