@@ -263,6 +263,9 @@ class FusedTrainLosses(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gd, gm, ge):
         net, eng = ctx.net, ctx.eng
+        if ctx.pose_ex is None:
+            raise RuntimeError("FusedTrainLosses: backward() ran already and released the exports (22 KB per pose); "
+                               "call the forward again instead of retain_graph=True")
         out = _FlatGrads(net)
         old_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = False
