@@ -13,7 +13,11 @@
  *     on it, nothing synchronises implicitly, the caller owns every buffer it passes in.
  *   - the library owns only what hangs off the handle (packed weight stream, per-CTA scratch).
  *   - a pose is 21 joints x 4 quaternion components, row-major, 84 floats = 336 bytes.
- *   - a handle is not thread-safe; use one handle per device per thread.
+ *   - a handle is not thread-safe; use one handle per device per thread, and drive it from ONE caller stream at a
+ *     time: the per-CTA scratch hanging off the handle is indexed by block only, so two launches of the same handle
+ *     must not overlap (launches on the same stream never do; pndf_project_host's two internal streams have their
+ *     own scratch copies).  Ordering that the library does handle across streams: a launch waits for the last weight
+ *     repack, and a weight repack waits for the last launch (events).
  */
 #ifndef PNDF_H_
 #define PNDF_H_
@@ -94,6 +98,30 @@ int pndf_project(pndf_handle* h, float* pose_dev, int64_t B, int steps, int reno
 int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out_host, float* dist_host,
                       int64_t B, int steps, int renorm);
 
+/* Multi-GPU projection run (BASELINE configs[2]: the loop of experiments/sample_poses.py:70-74 over a pose batch sharded
+ * across the GPUs of one node, ONE gather of the projected poses at the end; the reference itself has no distributed
+ * code).  pndf_project on this rank's shard, fused with the gather: the kernel's write-back also stores every projected
+ * tile (and its distance) straight into the gathered buffers of `n_peers` other GPUs through NVLink-mapped pointers
+ * (peer_pose_dev[r] / peer_dist_dev[r] = where THIS rank's slice starts inside peer r's gathered buffer; peer_dist_dev may
+ * be NULL), so the transfer overlaps the arithmetic tile by tile.  Completion on the peers = this stream reaching a
+ * pndf_peer_barrier.  n_peers <= 7. */
+int pndf_project_gather(pndf_handle* h, float* pose_dev, int64_t B, int steps, int renorm, float* dist_dev,
+                        float* const* peer_pose_dev, float* const* peer_dist_dev, int n_peers, void* stream);
+
+/* Peer memory for the fused gather, one process per GPU: cudaMalloc'ed, zero-filled buffer + its 64-byte cudaIpc handle
+ * (the caller ships the handle bytes to the other ranks -- torch.distributed in posendf_b200/dist.py); open / close map
+ * another rank's buffer into this process (peer access enabled lazily). */
+int pndf_peer_alloc(int device, size_t bytes, void** dev_ptr, unsigned char* handle64);
+int pndf_peer_open(int device, const unsigned char* handle64, void** dev_ptr);
+int pndf_peer_close(int device, void* dev_ptr);
+int pndf_peer_free(int device, void* dev_ptr);
+/* Barrier of the `world` ranks over peer memory, enqueued on `stream`: flags_dev[r] = rank r's flag array (world + 1
+ * uint32, zero-initialised, inside its peer buffer; flags_dev[rank] is the local one).  Stores `epoch` (increasing,
+ * same on all ranks) into every rank's array with release/system semantics -- ordered after all earlier peer stores of
+ * this stream -- and waits for every rank's epoch.  A rank that never arrives sets the local error slot [world] after
+ * ~10 s instead of hanging the GPU. */
+int pndf_peer_barrier(int device, uint32_t* const* flags_dev, int world, int rank, uint32_t epoch, void* stream);
+
 /* Motion-denoise prior term (experiments/motion_denoise.py:81-83,97-98):
  *   quat = axis_angle_to_quaternion(aa)   (pytorch3d 0.7.2 formula), dist = PoseNDF(quat),
  *   grad_aa = g_up[b] * d dist[b] / d aa[b]   (g_up NULL = ones).
@@ -157,6 +185,41 @@ int pndf_encoder_tangent(pndf_handle* h, const float* pose_dev, const float* v_d
 int pndf_encoder_param_grads(pndf_handle* h, const float* pose_dev, const float* v_dev, int64_t B, int normalise,
                              const float* up_first_dev, const float* up_tangent_dev, const float* up_second_dev,
                              float* grads_dev, void* stream);
+
+/* ---- training step, native end to end (model/posendf.py:78-99 losses, model/train_posendf.py:93-99 backward + Adam) ----
+ *
+ * pndf_train_losses: the per-pose part of the three losses on the outputs of pndf_forward_grad_export, one chunk of the
+ * batch at a time (B poses of B_total):
+ *   mode 0 (pose batch):     losses[0] = L1|MSE(dist, dist_gt) (l2 selects MSE), coef[b] = dLoss/ddist[b];
+ *                            with grad_dev (B*84): losses[1] = mean_{b,j} (|g_{b,j}| - 1)^2 and v[b] = dEikonal/dg[b]
+ *                            (zero sub-gradient where |g_{b,j}| == 0, as torch's norm backward)      posendf.py:85,89-96
+ *   mode 1 (manifold batch): losses[2] = mean |dist|                                                  posendf.py:86
+ * reset != 0 on the first chunk of a step.  losses_dev: 3 device floats, valid after the last chunk (running totals live in
+ * the handle); block partials are summed in a fixed order.  Nothing synchronises. */
+int pndf_train_losses(pndf_handle* h, const float* dist_dev, const float* dist_gt_dev, const float* grad_dev, int64_t B,
+                      int64_t B_total, int mode, int l2, int reset, float* coef_dev, float* v_dev, float* losses_dev, void* stream);
+
+/* loss.backward() for one exported chunk (model/train_posendf.py:98): accumulates into the flat gradient vector
+ * (reference parameter order, pndf_set_weights layout)
+ *     up * d/dtheta sum_b coef[b] dist(x_b)   +   w_eik * d/dtheta Eikonal      (first-order part of the Eikonal term:
+ *     exact for relu / lrelu; a softplus DFNet adds its second-order adjoint chain on top, posendf_b200/train.py)
+ * from the exports of pndf_forward_grad_export (dump_dev) and pndf_forward_tangent_export (dump_t_dev or NULL): split-K
+ * FFMA2 outer-product GEMMs for the six DFNet layers (wgrad_kernel), the last layer, the encoder reverse sweep, and a
+ * fixed-order reduction.  coef_dev NULL = the same weight `uniform` for every pose (manifold term).  up_dev / w_eik_dev are
+ * DEVICE scalars (the upstream gradients autograd hands to backward()); upz_dev = second-order adjoint of z0 (B*126,
+ * softplus DFNet) or NULL; v_dev = the pose tangent the tangent launch used.  overwrite != 0 stores instead of adding. */
+int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_dev, int normalise, const float* dump_dev,
+                          const float* dump_t_dev, const float* coef_dev, float uniform, const float* dist_dev, int64_t B,
+                          const float* up_dev, const float* w_eik_dev, const float* upz_dev, float* grad_flat_dev, int overwrite,
+                          void* stream);
+
+/* torch.optim.Adam(params, lr, betas, eps, weight_decay).step() (model/train_posendf.py:30,99) on the flat parameter /
+ * gradient / moment vectors, same operation order as torch; the same kernel writes the new values into the engine's packed
+ * weight buffers, so the next launch sees them without a repack.  grad_scale multiplies the gradient first (1 / world size
+ * after a summing all-reduce).  step counts from 1. */
+int pndf_adam_step(pndf_handle* h, float* param_flat_dev, const float* grad_flat_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                   size_t n, double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
+                   int64_t step, void* stream);
 
 /* Rotation formats on either side of the path: pytorch3d.transforms.axis_angle_to_quaternion / quaternion_to_axis_angle
  * (0.7.2; experiments/sample_poses.py:60,80, experiments/motion_denoise.py:81, model/load_data.py:108) on n rotations

@@ -137,8 +137,23 @@ def forward(params, pose, cfg, normalise=True):
     return dfnet_forward(params, z, cfg)[0]
 
 
-def forward_grad(params, pose, cfg, g_up=None, normalise=True):
-    """d (B,1) and  g_up[b] * dd_b/dpose_b  (B,21,4), closed form (SURVEY Appx A)."""
+def _dact_flip(pre, kind, beta, units):
+    """dact with the derivative branch of the listed units inverted (piecewise-linear activations only): what an fp32
+    evaluation computes when rounding puts a pre-activation that is ~0 on the other side of its kink."""
+    d = dact(pre, kind, beta)
+    if units:
+        assert kind in ("relu", "lrelu")
+        lo = pre.dtype.type(0.0 if kind == "relu" else LRELU_SLOPE)
+        for u in units:
+            d[:, u] = np.where(d[:, u] == 1, lo, pre.dtype.type(1))
+    return d
+
+
+def forward_grad(params, pose, cfg, g_up=None, normalise=True, flip=None):
+    """d (B,1) and  g_up[b] * dd_b/dpose_b  (B,21,4), closed form (SURVEY Appx A).
+    flip (tests only): {("df", l): [units], ("enc", i, 0|1): [units]} -- evaluate the gradient with those units on the other
+    branch of their kink (see _dact_flip)."""
+    flip = flip or {}
     x = np.asarray(pose).reshape(-1, NJ, 4)
     dt = x.dtype
     B = len(x)
@@ -157,7 +172,7 @@ def forward_grad(params, pose, cfg, g_up=None, normalise=True):
     g = g * dact(pres[-1], out_act_kind(cfg["df_act"]), cfg["df_beta"])
     g = g @ _p(params, f"dfnet.lin{L-1}.weight", dt)
     for l in range(L - 2, -1, -1):
-        g = (g * dact(pres[l], cfg["df_act"], cfg["df_beta"])) @ _p(params, f"dfnet.lin{l}.weight", dt)
+        g = (g * _dact_flip(pres[l], cfg["df_act"], cfg["df_beta"], flip.get(("df", l)))) @ _p(params, f"dfnet.lin{l}.weight", dt)
 
     if cfg["use_enc"]:
         fbar = [g[:, 6 * i:6 * i + 6].copy() for i in range(NJ)]
@@ -165,8 +180,8 @@ def forward_grad(params, pose, cfg, g_up=None, normalise=True):
         for i in range(NJ - 1, -1, -1):
             pre1, pre2 = ecache[i]
             w1 = _p(params, f"enc.net.{i}.net.0.weight", dt); w2 = _p(params, f"enc.net.{i}.net.2.weight", dt)
-            t = (fbar[i] * dact(pre2, cfg["enc_act"], cfg["enc_beta"])) @ w2
-            ubar = (t * dact(pre1, cfg["enc_act"], cfg["enc_beta"])) @ w1
+            t = (fbar[i] * _dact_flip(pre2, cfg["enc_act"], cfg["enc_beta"], flip.get(("enc", i, 1)))) @ w2
+            ubar = (t * _dact_flip(pre1, cfg["enc_act"], cfg["enc_beta"], flip.get(("enc", i, 0)))) @ w1
             qbar[:, i, :] += ubar[:, :4]
             if PARENTS[i] >= 0:
                 fbar[PARENTS[i]] += ubar[:, 4:10]
@@ -182,6 +197,46 @@ def forward_grad(params, pose, cfg, g_up=None, normalise=True):
     else:
         xbar = qbar
     return d, xbar
+
+
+def kink_units(params, pose, cfg, eps=1e-5, normalise=True):
+    """Piecewise-linear units of ONE pose whose pre-activation sits within eps of its kink, relative to the magnitude of the
+    terms it sums (sum |w_k z_k| + |b|, the scale an fp32 rounding error lives on): [(key, unit, margin)] sorted by margin,
+    key as in forward_grad's `flip`.  Evaluate in float64."""
+    x = np.asarray(pose, dtype=np.float64).reshape(1, NJ, 4)
+    q = normalise_columns(x)[0] if normalise else x
+    out = []
+
+    def scan(key, pre, zin, w, b, kind):
+        if kind == "softplus":
+            return
+        denom = np.abs(zin) @ np.abs(w).T + np.abs(b)
+        m = (np.abs(pre) / np.maximum(denom, 1e-300))[0]
+        out.extend((key, int(u), float(m[u])) for u in np.nonzero(m < eps)[0])
+
+    if cfg["use_enc"]:
+        feats = [None] * NJ
+        for i in range(NJ):
+            par = PARENTS[i]
+            u = q[:, i, :] if par < 0 else np.concatenate([q[:, i, :], feats[par]], axis=1)
+            w1 = _p(params, f"enc.net.{i}.net.0.weight", np.float64); b1 = _p(params, f"enc.net.{i}.net.0.bias", np.float64)
+            w2 = _p(params, f"enc.net.{i}.net.2.weight", np.float64); b2 = _p(params, f"enc.net.{i}.net.2.bias", np.float64)
+            pre1 = u @ w1.T + b1
+            scan(("enc", i, 0), pre1, u, w1, b1, cfg["enc_act"])
+            h = act(pre1, cfg["enc_act"], cfg["enc_beta"])
+            pre2 = h @ w2.T + b2
+            scan(("enc", i, 1), pre2, h, w2, b2, cfg["enc_act"])
+            feats[i] = act(pre2, cfg["enc_act"], cfg["enc_beta"])
+        z = np.concatenate(feats, axis=1)
+    else:
+        z = q.reshape(1, -1)
+    L = num_df_layers(params)
+    for l in range(L - 1):
+        w = _p(params, f"dfnet.lin{l}.weight", np.float64); b = _p(params, f"dfnet.lin{l}.bias", np.float64)
+        pre = z @ w.T + b
+        scan(("df", l), pre, z, w, b, cfg["df_act"])
+        z = act(pre, cfg["df_act"], cfg["df_beta"])
+    return sorted(out, key=lambda t: t[2])
 
 
 def project(params, pose, cfg, steps=10, renorm=False, return_traj=False):

@@ -5,9 +5,11 @@
 #include "pndf_denoise.cuh"
 #include "pndf_encoder_train.cuh"
 #include "pndf_train_ops.cuh"
+#include "pndf_wgrad.cuh"
 #include "pndf_knn.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -50,8 +52,15 @@ struct pndf_handle {
     bool w_pending = false;
     size_t off_bias[7];
     size_t off_w6 = 0, off_enc = 0;
-    float* d_scratch = nullptr;   // softplus derivative scratch, num_sms * kUnits * 32 floats
-    float* d_z0 = nullptr;        // encoder feature stash, num_sms * 128 * 32 floats
+    // per-CTA scratch (softplus derivatives: num_sms * kUnits * 32 floats; encoder feature stash: num_sms * 128 * 32
+    // floats), indexed by blockIdx only -- so every stream that may have a launch in flight needs its own copy:
+    // slot 0 = the caller's stream (a handle is driven from ONE caller stream, include/pndf.h), slots 1, 2 = the two
+    // pipeline streams of pndf_project_host (allocated on first use)
+    float* d_scratch[3] = {nullptr, nullptr, nullptr};
+    float* d_z0[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t use_event = nullptr;   // recorded after every launch: a repack on another stream waits for it (WAR on the weights)
+    cudaStream_t use_stream = nullptr;
+    bool used = false;
     int f0_slabs = 0, z0_rows = 0;
     int64_t launches = 0;
     // host pipeline (pndf_project_host)
@@ -59,6 +68,15 @@ struct pndf_handle {
     float* d_chunk[2] = {nullptr, nullptr};
     float* d_chunk_dist[2] = {nullptr, nullptr};
     int64_t chunk_poses = 0;
+    // training (pndf_train_losses / pndf_wgrad_accumulate / pndf_adam_step)
+    int32_t* d_pos[3] = {nullptr, nullptr, nullptr};   // flat parameter index -> slab-stream position (forward / reverse copy), small-buffer position
+    float* d_ws = nullptr;            // split-K workspace [slots][n_params]
+    int ws_slots = 0;
+    float* d_encrows = nullptr;       // encoder-gradient accumulators [2][kEncFloats]
+    float* d_loss_partial = nullptr;  // [blocks][2]
+    int loss_blocks = 0;
+    unsigned int* d_loss_counter = nullptr;
+    double* d_loss_totals = nullptr;  // [3]
     // denoise loop state (pndf_denoise_prior): raw gradient, Adam moments, dist
     float* d_dn[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t dn_poses = 0;
@@ -186,6 +204,8 @@ __global__ void pack_gather_kernel(const float* __restrict__ flat, const int32_t
 }
 
 int pack_on_device(pndf_handle* h, const float* d_flat, cudaStream_t st) {
+    // launches still reading the old weights on another stream must finish first
+    if (h->used && h->use_stream != st) CUDA_OK(cudaStreamWaitEvent(st, h->use_event, 0));
     pack_gather_kernel<<<h->num_sms * 4, 256, 0, st>>>(d_flat, h->d_map_w, h->d_wstream, h->wstream_floats);
     pack_gather_kernel<<<8, 256, 0, st>>>(d_flat, h->d_map_s, h->d_small, h->small_floats);
     CUDA_OK(cudaGetLastError());
@@ -220,18 +240,67 @@ int build_maps(pndf_handle* h) {
     CUDA_OK(cudaMalloc(&h->d_flat, n * sizeof(float)));
     CUDA_OK(cudaMemcpy(h->d_map_w, mw.data(), mw.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(h->d_map_s, ms.data(), ms.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    // inverse maps for the optimizer kernel: where does flat parameter i live in the packed buffers?
+    std::vector<int32_t> pos[3];
+    for (auto& v : pos) v.assign(n, -1);
+    for (size_t i = 0; i < mw.size(); ++i) {
+        if (mw[i] < 0) continue;
+        if (pos[0][mw[i]] < 0) pos[0][mw[i]] = (int32_t)i;
+        else if (pos[1][mw[i]] < 0) pos[1][mw[i]] = (int32_t)i;
+        else return fail("internal: a weight appears more than twice in the slab stream");
+    }
+    for (size_t i = 0; i < ms.size(); ++i)
+        if (ms[i] >= 0) pos[2][ms[i]] = (int32_t)i;
+    for (size_t i = 0; i < n; ++i)
+        if (pos[0][i] < 0 && pos[2][i] < 0) return fail("internal: a parameter is missing from the packed buffers");
+    for (int k = 0; k < 3; ++k) {
+        CUDA_OK(cudaMalloc(&h->d_pos[k], n * sizeof(int32_t)));
+        CUDA_OK(cudaMemcpy(h->d_pos[k], pos[k].data(), n * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
-int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st) {
+// Barrier between the GPUs of one node over peer memory: every rank owns a flag array [world + 1] inside its IPC buffer;
+// lane r stores `epoch` into rank r's array at index `rank` (release, system scope: everything this stream wrote to peer
+// memory before -- the fused gather stores of the preceding kernel -- is visible first) and then waits until rank r's
+// epoch has arrived in the local array.  Bounded spin: after ~10 s the error slot [world] is set instead of hanging.
+struct PeerFlags {
+    uint32_t* flags[kMaxPeers + 1];
+};
+__global__ void peer_barrier_kernel(PeerFlags f, int world, int rank, uint32_t epoch) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.flags[r] + rank), "r"(epoch) : "memory");
+    const uint32_t* mine = f.flags[rank] + r;
+    for (long long spin = 0;; ++spin) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        if (spin > (1LL << 26)) {
+            f.flags[rank][world] = 1u;
+            break;
+        }
+        __nanosleep(128);
+    }
+}
+
+int ensure_slot(pndf_handle* h, int slot) {
+    if (!h->d_z0[slot]) CUDA_OK(cudaMalloc(&h->d_z0[slot], (size_t)h->num_sms * 128 * 32 * sizeof(float)));
+    if (h->cfg.df_act == PNDF_ACT_SOFTPLUS && !h->d_scratch[slot])
+        CUDA_OK(cudaMalloc(&h->d_scratch[slot], (size_t)h->num_sms * kUnits * 32 * sizeof(float)));
+    return 0;
+}
+
+int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st, int slot = 0) {
     if (!h->have_weights) return fail("pndf_set_weights has not been called");
     if (p.B <= 0) return 0;
     p.wstream = h->d_wstream;
     for (int l = 0; l < 7; ++l) p.bias[l] = h->d_small + h->off_bias[l];
     p.w6 = h->d_small + h->off_w6;
     p.encw = h->cfg.use_enc ? h->d_small + h->off_enc : nullptr;
-    p.dscratch = h->d_scratch;
-    p.z0scratch = h->d_z0;
+    p.dscratch = h->d_scratch[slot];
+    p.z0scratch = h->d_z0[slot];
     p.ntiles = (int)((p.B + kTileM - 1) / kTileM);
     p.use_enc = h->cfg.use_enc; p.enc_act = h->cfg.enc_act; p.df_act = h->cfg.df_act;
     p.enc_beta = h->cfg.enc_beta; p.df_beta = h->cfg.df_beta;
@@ -245,6 +314,9 @@ int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st) {
     else
         pndf_fused_kernel<0><<<grid, kThreads, kSmTotal, st>>>(p);
     CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaEventRecord(h->use_event, st));
+    h->use_stream = st;
+    h->used = true;
     h->launches++;
     return 0;
 }
@@ -280,9 +352,8 @@ int pndf_create(const pndf_config* cfg, pndf_handle** out) {
     CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
     CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
     CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
-    CUDA_OK(cudaMalloc(&h->d_z0, (size_t)h->num_sms * 128 * 32 * sizeof(float)));
-    if (cfg->df_act == PNDF_ACT_SOFTPLUS)
-        CUDA_OK(cudaMalloc(&h->d_scratch, (size_t)h->num_sms * kUnits * 32 * sizeof(float)));
+    if (ensure_slot(h, 0)) { pndf_destroy(h); return 1; }
+    if (cudaEventCreateWithFlags(&h->use_event, cudaEventDisableTiming) != cudaSuccess) { pndf_destroy(h); return fail("cudaEventCreate failed"); }
     if (build_maps(h)) { pndf_destroy(h); return 1; }
     *out = h;
     return 0;
@@ -297,9 +368,18 @@ int pndf_destroy(pndf_handle* h) {
     cudaFree(h->d_map_s);
     cudaFree(h->d_flat);
     if (h->w_event) cudaEventDestroy(h->w_event);
-    cudaFree(h->d_scratch);
-    cudaFree(h->d_z0);
+    if (h->use_event) cudaEventDestroy(h->use_event);
+    for (int i = 0; i < 3; ++i) {
+        cudaFree(h->d_scratch[i]);
+        cudaFree(h->d_z0[i]);
+    }
     for (int i = 0; i < 4; ++i) cudaFree(h->d_dn[i]);
+    for (int i = 0; i < 3; ++i) cudaFree(h->d_pos[i]);
+    cudaFree(h->d_ws);
+    cudaFree(h->d_encrows);
+    cudaFree(h->d_loss_partial);
+    cudaFree(h->d_loss_counter);
+    cudaFree(h->d_loss_totals);
     for (int i = 0; i < 2; ++i) {
         if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
         cudaFree(h->d_chunk[i]);
@@ -360,6 +440,79 @@ int pndf_project(pndf_handle* h, float* pose_dev, int64_t B, int steps, int reno
     return launch(h, p, 1, (cudaStream_t)stream);
 }
 
+int pndf_project_gather(pndf_handle* h, float* pose_dev, int64_t B, int steps, int renorm, float* dist_dev,
+                        float* const* peer_pose_dev, float* const* peer_dist_dev, int n_peers, void* stream) {
+    if (!h) return fail("null handle");
+    if (steps < 1) return fail("steps must be >= 1");
+    if (n_peers < 0 || n_peers > kMaxPeers) return fail("pndf_project_gather: at most 7 peers (8 GPUs of one node)");
+    if (n_peers > 0 && !peer_pose_dev) return fail("null argument");
+    if (B == 0) return 0;
+    if (B < 0 || !pose_dev) return fail("null argument");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    KParams p{};
+    p.pose_in = pose_dev; p.pose_out = pose_dev; p.dist = dist_dev; p.B = B; p.steps = steps; p.do_step = 1;
+    p.renorm = renorm; p.normalise = 1; p.input_kind = IN_QUAT;
+    p.n_peers = n_peers;
+    for (int r = 0; r < n_peers; ++r) {
+        if (!peer_pose_dev[r] || (reinterpret_cast<uintptr_t>(peer_pose_dev[r]) & 15)) return fail("pndf_project_gather: peer pointers must be 16-byte aligned");
+        p.peer_pose[r] = peer_pose_dev[r];
+        p.peer_dist[r] = peer_dist_dev ? peer_dist_dev[r] : nullptr;
+    }
+    return launch(h, p, 1, (cudaStream_t)stream);
+}
+
+// ---- peer memory (one process per GPU): cudaMalloc + cudaIpc handles; the handle bytes travel through the caller's
+// own channel (torch.distributed all_gather in posendf_b200/dist.py)
+int pndf_peer_alloc(int device, size_t bytes, void** dev_ptr, unsigned char* handle64) {
+    if (!dev_ptr || !handle64 || bytes == 0) return fail("pndf_peer_alloc: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CUDA_OK(cudaSetDevice(device));
+    void* ptr = nullptr;
+    CUDA_OK(cudaMalloc(&ptr, bytes));
+    CUDA_OK(cudaMemset(ptr, 0, bytes));
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, ptr);
+    if (e != cudaSuccess) {
+        cudaFree(ptr);
+        return fail(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    memcpy(handle64, &hd, 64);
+    *dev_ptr = ptr;
+    return 0;
+}
+int pndf_peer_open(int device, const unsigned char* handle64, void** dev_ptr) {
+    if (!dev_ptr || !handle64) return fail("pndf_peer_open: bad argument");
+    CUDA_OK(cudaSetDevice(device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    CUDA_OK(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int pndf_peer_close(int device, void* dev_ptr) {
+    if (!dev_ptr) return 0;
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+int pndf_peer_free(int device, void* dev_ptr) {
+    if (!dev_ptr) return 0;
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaFree(dev_ptr));
+    return 0;
+}
+int pndf_peer_barrier(int device, uint32_t* const* flags_dev, int world, int rank, uint32_t epoch, void* stream) {
+    if (!flags_dev || world < 1 || world > kMaxPeers + 1 || rank < 0 || rank >= world) return fail("pndf_peer_barrier: bad argument");
+    CUDA_OK(cudaSetDevice(device));
+    PeerFlags f{};
+    for (int r = 0; r < world; ++r) {
+        if (!flags_dev[r]) return fail("pndf_peer_barrier: null flag array");
+        f.flags[r] = flags_dev[r];
+    }
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, world, rank, epoch);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int pndf_prior_grad(pndf_handle* h, const float* aa_dev, int64_t B, const float* g_up_dev, float* dist_dev,
                     float* grad_aa_dev, void* stream) {
     if (!h) return fail("null handle");
@@ -388,6 +541,7 @@ int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out
         }
         h->chunk_poses = chunk;
     }
+    if (ensure_slot(h, 1) || ensure_slot(h, 2)) return 1;   // the two streams overlap: each needs its own per-CTA scratch
     int which = 0;
     for (int64_t off = 0; off < B; off += chunk, which ^= 1) {
         const int64_t nb = std::min(chunk, B - off);
@@ -396,7 +550,7 @@ int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out
         KParams p{};
         p.pose_in = h->d_chunk[which]; p.pose_out = h->d_chunk[which]; p.dist = h->d_chunk_dist[which]; p.B = nb;
         p.steps = steps; p.do_step = 1; p.renorm = renorm; p.normalise = 1; p.input_kind = IN_QUAT;
-        if (launch(h, p, 1, st)) return 1;
+        if (launch(h, p, 1, st, 1 + which)) return 1;
         CUDA_OK(cudaMemcpyAsync(pose_out_host + off * 84, h->d_chunk[which], nb * 84 * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (dist_host) CUDA_OK(cudaMemcpyAsync(dist_host + off, h->d_chunk_dist[which], nb * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
@@ -553,6 +707,146 @@ int pndf_softplus_adjoint(int device, const float* z_next_dev, const float* zdot
     const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
     softplus_adjoint_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pndf_train_losses(pndf_handle* h, const float* dist_dev, const float* dist_gt_dev, const float* grad_dev, int64_t B,
+                      int64_t B_total, int mode, int l2, int reset, float* coef_dev, float* v_dev, float* losses_dev, void* stream) {
+    if (!h) return fail("null handle");
+    if (B <= 0 || B_total < B || !dist_dev || !losses_dev) return fail("pndf_train_losses: bad argument");
+    if (mode != 0 && mode != 1) return fail("pndf_train_losses: mode must be 0 (pose batch) or 1 (manifold batch)");
+    if (mode == 0 && (!dist_gt_dev || !coef_dev)) return fail("pndf_train_losses: pose mode needs dist_gt and coef");
+    if (mode == 0 && grad_dev && !v_dev) return fail("pndf_train_losses: Eikonal term needs the tangent output");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    const int blocks = (int)((B + 255) / 256);
+    if (h->loss_blocks < blocks) {
+        cudaFree(h->d_loss_partial);
+        h->d_loss_partial = nullptr;
+        CUDA_OK(cudaMalloc(&h->d_loss_partial, (size_t)blocks * 2 * sizeof(float)));
+        h->loss_blocks = blocks;
+    }
+    if (!h->d_loss_counter) {
+        CUDA_OK(cudaMalloc(&h->d_loss_counter, sizeof(unsigned int)));
+        CUDA_OK(cudaMemset(h->d_loss_counter, 0, sizeof(unsigned int)));
+        CUDA_OK(cudaMalloc(&h->d_loss_totals, 3 * sizeof(double)));
+        CUDA_OK(cudaMemset(h->d_loss_totals, 0, 3 * sizeof(double)));
+    }
+    LossParams p{};
+    p.dist = dist_dev; p.dist_gt = dist_gt_dev; p.grad = grad_dev; p.coef = coef_dev; p.v = v_dev;
+    p.partial = h->d_loss_partial; p.counter = h->d_loss_counter; p.totals = h->d_loss_totals; p.losses = losses_dev;
+    p.B = B; p.inv_n = 1.0 / (double)B_total; p.mode = mode; p.l2 = l2; p.reset = reset;
+    if (reset && mode == 0) CUDA_OK(cudaMemsetAsync(losses_dev, 0, 3 * sizeof(float), (cudaStream_t)stream));
+    train_loss_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_dev, int normalise, const float* dump_dev,
+                          const float* dump_t_dev, const float* coef_dev, float uniform, const float* dist_dev, int64_t B,
+                          const float* up_dev, const float* w_eik_dev, const float* upz_dev, float* grad_flat_dev, int overwrite,
+                          void* stream) {
+    if (!h) return fail("null handle");
+    if (B == 0) return 0;
+    if (B < 0 || !pose_dev || !dump_dev || !dist_dev || !up_dev || !grad_flat_dev) return fail("pndf_wgrad_accumulate: null argument");
+    if (!h->have_weights) return fail("pndf_set_weights has not been called");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_params = param_count(&h->cfg);
+    const int ksplits = (int)((B + kWgKC - 1) / kWgKC);
+    if (h->ws_slots < ksplits) {
+        cudaFree(h->d_ws);
+        h->d_ws = nullptr;
+        CUDA_OK(cudaMalloc(&h->d_ws, (size_t)ksplits * n_params * sizeof(float)));
+        h->ws_slots = ksplits;
+    }
+    if (!h->d_encrows) CUDA_OK(cudaMalloc(&h->d_encrows, 2 * kEncFloats * sizeof(float)));
+    static bool attr_set[64] = {};
+    if (h->cfg.device < 64 && !attr_set[h->cfg.device]) {
+        CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+        attr_set[h->cfg.device] = true;
+    }
+    // flat parameter offsets (reference order): [encoder] W0 b0 W1 b1 ... W6 b6
+    const int in0 = h->cfg.in_dim;
+    const int widths[8] = {in0, 256, 512, 1024, 512, 256, 64, 1};
+    long long off = h->cfg.use_enc ? kEncFloats : 0, w_off[7], b_off[7];
+    for (int l = 0; l < 7; ++l) {
+        w_off[l] = off; off += (long long)widths[l + 1] * widths[l];
+        b_off[l] = off; off += widths[l + 1];
+    }
+    // export column map: layer inputs z_l, adjoints of pre_l
+    const int z_col[7] = {0, 128, 384, 896, 1920, 2432, 2688};
+    const int a_col[6] = {5120, 4608, 3584, 3072, 2816, 2752};
+    WgParams p{};
+    p.dump = dump_dev; p.dump_t = dump_t_dev; p.coef = coef_dev; p.up = up_dev; p.w_eik = w_eik_dev; p.uniform = uniform;
+    p.ws = h->d_ws; p.B = B; p.n_params = (long long)n_params; p.slot0 = 0; p.nprob = 6;
+    int tiles = 0;
+    // big layers first: their CTAs start first inside every K-split
+    const int order[6] = {2, 3, 1, 4, 0, 5};
+    for (int i = 0; i < 6; ++i) {
+        const int l = order[i];
+        WgProblem& q = p.prob[i];
+        q.a_col = a_col[l]; q.z_col = z_col[l]; q.n_out = widths[l + 1]; q.n_in = widths[l];
+        q.m_tiles = (q.n_out + kWgTile - 1) / kWgTile; q.n_tiles = (q.n_in + kWgTile - 1) / kWgTile;
+        q.tile0 = tiles; q.w_off = w_off[l]; q.b_off = b_off[l];
+        tiles += q.m_tiles * q.n_tiles;
+    }
+    if (order_after_weights(h, st)) return 1;
+    wgrad_kernel<<<dim3((unsigned)tiles, (unsigned)ksplits), kWgThreads, kWgSmem, st>>>(p);
+    CUDA_OK(cudaGetLastError());
+    WgLastParams lp{};
+    lp.dump = dump_dev; lp.dump_t = dump_t_dev; lp.coef = coef_dev; lp.up = up_dev; lp.w_eik = w_eik_dev; lp.dist = dist_dev;
+    lp.uniform = uniform; lp.ws = h->d_ws; lp.B = B; lp.n_params = (long long)n_params; lp.w6_off = w_off[6]; lp.b6_off = b_off[6];
+    lp.slot0 = 0; lp.z6_col = z_col[6]; lp.softplus = (h->cfg.df_act == PNDF_ACT_SOFTPLUS); lp.beta = h->cfg.df_beta;
+    wgrad_last_kernel<<<(unsigned)ksplits, 256, 0, st>>>(lp);
+    CUDA_OK(cudaGetLastError());
+    int n_enc_rows = 0;
+    if (h->cfg.use_enc) {
+        CUDA_OK(cudaMemsetAsync(h->d_encrows, 0, 2 * kEncFloats * sizeof(float), st));
+        EncTrainParams ep{};
+        ep.x = pose_dev; ep.v = (w_eik_dev || upz_dev) ? v_dev : nullptr; ep.encw = h->d_small + h->off_enc; ep.upz = upz_dev;
+        ep.g0 = dump_dev + 5376; ep.g0_ld = kDumpRows; ep.coef = coef_dev; ep.uniform = uniform; ep.up = up_dev;
+        ep.weik = dump_t_dev ? w_eik_dev : nullptr;
+        ep.grads = h->d_encrows; ep.B = B; ep.normalise = normalise; ep.act = h->cfg.enc_act; ep.beta = h->cfg.enc_beta; ep.use_enc = 1;
+        enc_grad_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(ep);
+        CUDA_OK(cudaGetLastError());
+        n_enc_rows = (ep.weik || ep.upz) ? 2 : 1;
+        h->launches++;
+    }
+    wgrad_reduce_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, st>>>(h->d_ws, ksplits, (long long)n_params,
+                                                                           h->cfg.use_enc ? kEncFloats : 0, h->d_encrows, n_enc_rows,
+                                                                           grad_flat_dev, overwrite);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 3;
+    return 0;
+}
+
+int pndf_adam_step(pndf_handle* h, float* param_flat_dev, const float* grad_flat_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                   size_t n, double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
+                   int64_t step, void* stream) {
+    if (!h) return fail("null handle");
+    if (!param_flat_dev || !grad_flat_dev || !exp_avg_dev || !exp_avg_sq_dev) return fail("pndf_adam_step: null argument");
+    if (n != param_count(&h->cfg)) return fail("pndf_adam_step: wrong parameter count");
+    if (step < 1) return fail("pndf_adam_step: step counts from 1");
+    CUDA_OK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // launches of other streams still reading the packed weights must finish first (same rule as a repack)
+    if (h->used && h->use_stream != st) CUDA_OK(cudaStreamWaitEvent(st, h->use_event, 0));
+    AdamStepParams p{};
+    p.param = param_flat_dev; p.grad = grad_flat_dev; p.m = exp_avg_dev; p.v = exp_avg_sq_dev; p.n = (long long)n;
+    p.lr_over_bias1 = (float)(lr / (1.0 - std::pow(beta1, (double)step)));
+    p.bias2_sqrt = (float)std::sqrt(1.0 - std::pow(beta2, (double)step));
+    p.one_minus_beta1 = (float)(1.0 - beta1); p.beta2 = (float)beta2; p.one_minus_beta2 = (float)(1.0 - beta2);
+    p.eps = (float)eps; p.weight_decay = (float)weight_decay; p.grad_scale = (float)grad_scale;
+    p.pos_a = h->d_pos[0]; p.pos_b = h->d_pos[1]; p.pos_s = h->d_pos[2]; p.wstream = h->d_wstream; p.small = h->d_small;
+    adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    CUDA_OK(cudaGetLastError());
+    if (!h->w_event) CUDA_OK(cudaEventCreateWithFlags(&h->w_event, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(h->w_event, st));
+    h->w_stream = st;
+    h->w_pending = true;
+    h->have_weights = true;
+    h->launches++;
     return 0;
 }
 

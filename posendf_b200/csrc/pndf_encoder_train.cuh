@@ -25,6 +25,15 @@ struct EncTrainParams {
     const float* up1;      // B x 126 or nullptr
     const float* upt;      // B x 126 or nullptr
     const float* upz;      // B x 126 or nullptr
+    // the same three vectors formed on the fly from the launch-1 export (no intermediate tensors): g0 = dd/dz0 per pose
+    // (row stride g0_ld), up1 = up * coef_b * g0 (coef == nullptr: `uniform` for every pose), upt = w_eik * g0
+    const float* g0;       // or nullptr: use up1 / upt above
+    long long g0_ld;
+    const float* coef;     // [B] or nullptr
+    float uniform;
+    const float* up;       // device scalar
+    const float* weik;     // device scalar or nullptr (no Eikonal objective)
+    int in_dim;            // 126 (row stride of upz)
     float* zdot_tiles;     // [tile][128][32] (tangent kernel)
     float* grads;          // 2 x 3516 (grad kernel), accumulated with atomics: caller zeroes
     long long B;
@@ -194,7 +203,14 @@ __global__ void __launch_bounds__(128) enc_grad_kernel(const EncTrainParams p) {
     const bool live = b < p.B;
     const long long bb = live ? b : 0;
     const int lane = threadIdx.x & 31;
-    const bool set1 = (p.upt != nullptr) || (p.upz != nullptr);     // uniform: the Eikonal objective is present
+    const bool from_dump = (p.g0 != nullptr);
+    const bool set1 = from_dump ? ((p.weik != nullptr) || (p.upz != nullptr))
+                                : ((p.upt != nullptr) || (p.upz != nullptr));     // uniform: the Eikonal objective is present
+    float c1 = 0.0f, ce = 0.0f;
+    if (from_dump && live) {
+        c1 = __ldg(p.up) * (p.coef ? __ldg(p.coef + bb) : p.uniform);
+        ce = p.weik ? __ldg(p.weik) : 0.0f;
+    }
     float q[84], qd[84], feat[21][6], featd[21][6];
     load_q_qd(p, bb, q, qd);
     for (int i = 0; i < 21; ++i) {
@@ -209,9 +225,15 @@ __global__ void __launch_bounds__(128) enc_grad_kernel(const EncTrainParams p) {
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
             const long long o = bb * 126 + i * 6 + r;
-            fb0[i][r] = (live && p.up1) ? p.up1[o] : 0.0f;
+            if (from_dump) {
+                const float g = live ? __ldg(p.g0 + bb * p.g0_ld + i * 6 + r) : 0.0f;
+                fb0[i][r] = c1 * g;
+                fdb1[i][r] = ce * g;
+            } else {
+                fb0[i][r] = (live && p.up1) ? p.up1[o] : 0.0f;
+                fdb1[i][r] = (live && p.upt) ? p.upt[o] : 0.0f;
+            }
             fb1[i][r] = (live && p.upz) ? p.upz[o] : 0.0f;
-            fdb1[i][r] = (live && p.upt) ? p.upt[o] : 0.0f;
         }
     for (int i = 20; i >= 0; --i) {
         const int par = c_parent[i];

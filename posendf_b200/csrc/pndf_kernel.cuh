@@ -41,6 +41,7 @@ constexpr int kXS = 85;               // padded row stride of the pose tile
 constexpr int kMaskStride = 2656;     // bytes per pose-group plane of the derivative bit masks
 constexpr int kUnits = 2624;          // hidden units of the DFNet (256+512+1024+512+256+64)
 constexpr int kEncFloats = 3516;
+constexpr int kMaxPeers = 7;          // other GPUs of one NVSwitch node
 constexpr int kEncStageRow = 256;     // encoder weights are parked in X rows [256, 366) while the encoder runs
 
 // unit offsets (mask / scratch index) of each hidden layer output z1..z6
@@ -81,6 +82,12 @@ struct KParams {
                               // relu, lrelu: [tile][4][kMaskStride] bit masks; softplus: [tile][kUnits][32] fp32
     int dump_all;             // 0: first tile only (debug hook)   1: every tile (training: exports for the weight gradients)
     const float* tan_in;      // MODE 2: tangent of the DFNet input, [tile][128][32] floats
+    // fused gather (multi-GPU projection runs): the write-back also stores every projected tile -- and its distances --
+    // into the gathered buffers of up to kMaxPeers other GPUs through NVLink-mapped (cudaIpc) pointers, each already
+    // offset to this rank's slice.  The transfer rides under the FMA work of the following tiles.
+    float* peer_pose[kMaxPeers];
+    float* peer_dist[kMaxPeers];
+    int n_peers;
     long long B;
     int ntiles;
     int steps;                // projection steps fused in this launch (>=1)
@@ -940,7 +947,11 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                     float gu = 1.0f;
                     if (p.g_up != nullptr && m < nvalid) gu = __ldg(p.g_up + pose0 + m);
                     dval[32 + m] = gu * dv;
-                    if (p.dist != nullptr && m < nvalid && st == p.steps - 1) p.dist[pose0 + m] = d;
+                    if (m < nvalid && st == p.steps - 1) {
+                        if (p.dist != nullptr) p.dist[pose0 + m] = d;
+                        for (int r = 0; r < p.n_peers; ++r)
+                            if (p.peer_dist[r] != nullptr) p.peer_dist[r][pose0 + m] = d;
+                    }
                 }
             }
             if (MODE == 2) gemm_bar();   // X (z6 / its tangent) is reloaded by the next pass
@@ -1101,10 +1112,13 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 }
             }
             if (p.pose_out != nullptr) {
-                float* dst = p.pose_out + pose0 * 84;
-                for (int idx = tid; idx < nvalid * 84; idx += kGemmThreads) {
-                    const int m = idx / 84, e = idx - m * 84;
-                    dst[idx] = xs[m * kXS + e];
+                // 16-byte stores (a pose row is 21 float4, a tile starts 16-byte aligned); the same values go to every peer
+                for (int i4 = tid; i4 < nvalid * 21; i4 += kGemmThreads) {
+                    const int m = i4 / 21, e = (i4 - m * 21) * 4;
+                    const float* src = xs + m * kXS + e;
+                    const float4 v = make_float4(src[0], src[1], src[2], src[3]);
+                    reinterpret_cast<float4*>(p.pose_out + pose0 * 84)[i4] = v;
+                    for (int r = 0; r < p.n_peers; ++r) reinterpret_cast<float4*>(p.peer_pose[r] + pose0 * 84)[i4] = v;
                 }
             }
         }

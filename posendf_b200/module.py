@@ -17,12 +17,13 @@ load_state_dict(), parameters() and .to() behave as in the reference; the packed
 inside the engine is a cache that is rebuilt whenever a parameter tensor changes version.
 
 train=True (model/posendf.py:78-99: dist + manifold + Eikonal losses and their parameter gradients, including the
-Eikonal double backward) runs on the fused path as well: posendf_b200/train.py (three fused launches exporting the
-operands of the weight-gradient GEMMs, cuBLAS for those batch reductions, two small kernels for the 3 516-parameter
-encoder; no torch autograd), checked against the reference's autograd to ~1e-6 and 1.7x faster than it on B200
-(17 vs 30 ms per 32 768+32 768-sample step incl. Adam, lrelu).  It needs CUDA parameters and raises otherwise.
-opt['train']['fused_train'] = False selects plain torch autograd over the same submodules instead; that mode exists
-as the cross-check the tests compare the fused step with, not as a fallback.
+Eikonal double backward) runs natively as well (posendf_b200/train.py): fused launches exporting the operands of the
+weight-gradient reductions, a loss kernel, the split-K FFMA2 weight-gradient kernel, two small encoder kernels -- no torch
+autograd graph, no library GEMM for relu / lrelu (a softplus DFNet still evaluates its second-order adjoint chain with
+cuBLAS).  Gradients land in ONE flat buffer in the reference's parameter order; every `p.grad` is a view of it, and
+posendf_b200.optim.FusedAdam updates the flat parameter buffer and the engine's packed weights in one kernel.  It needs
+CUDA parameters and raises otherwise.  (The torch-autograd restatement of this forward that the tests cross-check
+against lives in tests/autograd_crosscheck.py, not here.)
 """
 from __future__ import annotations
 
@@ -132,9 +133,10 @@ class PoseNDF(nn.Module):
                          enc_beta=float(m["StrEnc"].get("beta", 100.0)), df_act=m["DFNet"]["act"],
                          df_beta=float(m["DFNet"].get("beta", 100.0)), in_dim=int(m["DFNet"]["in_dim"]),
                          dims=tuple(int(d) for d in m["DFNet"]["dims"]))
-        # train=True: the fused-kernel path (posendf_b200/train.py) unless opt['train']['fused_train'] = False asks for the
-        # plain torch-autograd cross-check over the same parameters
-        self._fused_train = bool(opt["train"].get("fused_train", True))
+        self._flat_param = None        # set by flatten_parameters_(): all parameters as views of one buffer
+        self._flat_grad = None         # flat gradient buffer (reference parameter order); p.grad are views of it
+        self._grad_views = None
+        self._grad_fresh = True        # next backward() overwrites the flat gradient instead of accumulating
         self._engine = None
         self._engine_key = None
         self._weights_sig = None
@@ -176,6 +178,60 @@ class PoseNDF(nn.Module):
                 self._engine.set_weights_device(torch.cat([p.detach().reshape(-1).float() for p in params]))
             self._weights_sig = sig
         return self._engine
+
+    # ------------------------------------------------------------------ flat parameter / gradient storage (training)
+    def flat_grad(self):
+        """the flat fp32 gradient vector (reference parameter order) on the parameters' device, with one view per parameter"""
+        params = self._ordered_params()
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        if self._flat_grad is None or self._flat_grad.device != dev or self._flat_grad.numel() != n:
+            self._flat_grad = torch.empty(n, device=dev, dtype=torch.float32)
+            self._grad_views, off = [], 0
+            for p in params:
+                self._grad_views.append(self._flat_grad[off:off + p.numel()].view(p.shape))
+                off += p.numel()
+            self._grad_fresh = True
+        return self._flat_grad
+
+    def grads_attached(self):
+        """True if every p.grad is the matching view of the flat gradient buffer (then backward() accumulates into it)"""
+        if self._flat_grad is None:
+            return False
+        return all(p.grad is not None and p.grad.data_ptr() == v.data_ptr() for p, v in zip(self._ordered_params(), self._grad_views))
+
+    def attach_grads(self):
+        self.flat_grad()
+        for p, v in zip(self._ordered_params(), self._grad_views):
+            p.grad = v
+
+    def flatten_parameters_(self):
+        """Re-seat every parameter as a view of ONE flat fp32 buffer (reference order), so that the fused optimizer kernel
+        and the data-parallel all-reduce work on a single contiguous vector.  state_dict / load_state_dict keep working
+        (they copy in place); .to() / .double() afterwards un-flatten (call this again)."""
+        params = self._ordered_params()
+        if self._flat_param is not None:
+            off, ok = 0, True
+            for p in params:
+                ok = ok and p.data_ptr() == self._flat_param.data_ptr() + 4 * off and p.dtype == torch.float32
+                off += p.numel()
+            if ok:
+                return self._flat_param
+        dev = params[0].device
+        flat = torch.cat([p.detach().reshape(-1).float() for p in params]).to(dev)
+        off = 0
+        for p in params:
+            p.data = flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self._flat_param = flat
+        self._weights_sig = None
+        return flat
+
+    def invalidate(self):
+        """Force a repack of the engine's weight copy on the next call.  The cache key is (data_ptr, _version) of every
+        parameter; writes through `p.data` (p.data.copy_, EMA / clipping code) do not bump _version -- call this after
+        them.  load_state_dict and optimizer steps bump the version and need nothing."""
+        self._weights_sig = None
 
     def distance(self, pose, normalise=True):
         """(B,1) distances on the module's device; differentiable w.r.t. `pose` (first order)."""
@@ -224,31 +280,13 @@ class PoseNDF(nn.Module):
     def forward(self, pose, dist_gt=None, man_poses=None, train=True, eikonal=0.0):
         if not train:
             return {"dist_pred": self.distance(pose)}
-        if self._fused_train:
-            if not next(self.parameters()).is_cuda:
-                raise RuntimeError("posendf_b200.PoseNDF: the fused train step needs CUDA parameters; there is no CPU "
-                                   "fallback (opt['train']['fused_train']=False selects the torch-autograd cross-check)")
-            from .train import train_forward
-            pose = pose.to(device=self.device).reshape(-1, 21, 4)
-            pose.requires_grad = True                      # the reference does this in place (model/posendf.py:66)
-            return train_forward(self, pose.detach(), dist_gt, man_poses, eikonal)
-        return self._train_forward(pose, dist_gt, man_poses, eikonal)
-
-    def _train_forward(self, pose, dist_gt, man_poses, eikonal):
-        # torch autograd over the parameter submodules (cuBLAS), not the fused kernel: see module docstring
+        if not next(self.parameters()).is_cuda:
+            raise RuntimeError("posendf_b200.PoseNDF: the train step runs only as fused CUDA kernels and needs CUDA parameters; "
+                               "there is no CPU fallback")
+        from .train import train_forward
         pose = pose.to(device=self.device).reshape(-1, 21, 4)
-        pose.requires_grad = True
-        dist_gt = dist_gt.to(device=self.device).reshape(-1)
-        q = nn.functional.normalize(pose, dim=1)
-        dist_pred = self.dfnet(self.enc(q) if self.enc is not None else q)
-        man = man_poses.to(device=self.device).reshape(-1, 21, 4)
-        dist_man = self.dfnet(self.enc(man) if self.enc is not None else man)
-        loss = self.loss_l1(dist_pred[:, 0], dist_gt)
-        if eikonal > 0.0:
-            (g,) = torch.autograd.grad(dist_pred, pose, torch.ones_like(dist_pred), create_graph=True, retain_graph=True)
-            eik = ((g.norm(2, dim=-1) - 1) ** 2).mean()
-            return loss, {"dist": loss, "man_loss": dist_man.abs().mean(), "eikonal": eik}
-        return loss, {"dist": loss}
+        pose.requires_grad = True                      # the reference does this in place (model/posendf.py:66)
+        return train_forward(self, pose.detach(), dist_gt, man_poses, eikonal)
 
 
 def gradient(inputs, outputs):

@@ -17,6 +17,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device AND the built library; on a CPU box they are skipped, not failed (they stay
+    selected under -m gpu on the B200 box, where a missing libpndf.so is an error, not a skip)."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200); run with -m gpu on the GPU box")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 def golden_case_names():
     skip = {"parents", "normalise", "knn_rerank"}
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
@@ -59,19 +71,56 @@ def per_pose_rel(a, b):
     return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-300)
 
 
-def assert_grad_parity(g, g64, tol=1e-5, outlier_frac=0.02, median_tol=4e-6):
+OUTLIER_CAP = 0.25          # no pose may be further off than this, kink or not
+
+
+def explain_by_kink_flips(g_pose, params, pose, cfg, tol, normalise=True, eps=1e-5, max_units=4):
+    """Is this pose's gradient the fp64 gradient with some of its near-kink units (oracle.kink_units, |pre| within eps of 0)
+    on the other branch?  Tries every subset of the (at most max_units) closest ones.  Returns (ok, units, best error)."""
+    from itertools import combinations
+    from oracle import posendf_numpy as onp
+    p64 = {k: np.asarray(v, dtype=np.float64) for k, v in params.items()}
+    x = np.asarray(pose, dtype=np.float64).reshape(1, 21, 4)
+    units = onp.kink_units(p64, x, cfg, eps=eps, normalise=normalise)[:max_units]
+    best = np.inf
+    for r in range(1, len(units) + 1):
+        for sub in combinations(units, r):
+            flip = {}
+            for key, u, _ in sub:
+                flip.setdefault(key, []).append(u)
+            _, g = onp.forward_grad(p64, x, cfg, normalise=normalise, flip=flip)
+            best = min(best, per_pose_rel(np.asarray(g_pose).reshape(1, -1), g.reshape(1, -1))[0])
+            if best < tol:
+                return True, sub, best
+    return False, units, best
+
+
+def assert_grad_parity(g, g64, tol=1e-5, outlier_frac=0.02, median_tol=4e-6, explain=None):
     """Gradient parity with fp64 adjudication.  A piecewise-linear unit sitting on its kink flips its mask
-    between ANY two fp32 evaluations (the reference's own fp32 run shows the same poses as outliers vs its
+    between ANY two fp32 evaluations (the reference's own fp32 run shows the same kind of outliers vs its
     fp64 run, SURVEY 7 / Appx D), which perturbs that whole pose's gradient; such poses are allowed up to
-    `outlier_frac`, everything else must be within `tol` norm-wise."""
+    `outlier_frac`, everything else must be within `tol` norm-wise.  Outliers are bounded (OUTLIER_CAP) and -- with
+    explain = (params, poses, cfg[, normalise]) -- each one must be reproduced to `tol` by the fp64 oracle with a
+    near-kink unit (|pre| within 1e-5 of zero) flipped: a kink flip, not an arithmetic error."""
     e = per_pose_rel(g, g64)
     assert np.median(e) < median_tol, f"median per-pose grad error {np.median(e):.3e}"
-    assert (e > tol).mean() <= outlier_frac, f"{(e > tol).sum()} of {len(e)} poses above {tol} (max {e.max():.3e})"
+    out = np.nonzero(e > tol)[0]
+    assert len(out) <= outlier_frac * len(e), f"{len(out)} of {len(e)} poses above {tol} (max {e.max():.3e})"
+    assert e.max() <= OUTLIER_CAP, f"outlier magnitude {e.max():.3e} above the cap"
+    if explain is not None and len(out):
+        params, poses, cfg = explain[:3]
+        normalise = explain[3] if len(explain) > 3 else True
+        assert cfg["df_act"] != "softplus" or cfg["enc_act"] != "softplus", "a smooth network has no kinks to blame"
+        gg = np.asarray(g).reshape(len(e), -1)
+        for b in out:
+            ok, units, best = explain_by_kink_flips(gg[b], params, np.asarray(poses)[b], cfg, tol, normalise)
+            assert ok, f"pose {b}: error {e[b]:.3e} is not a kink flip (near-kink units {units}, best {best:.3e})"
 
 
 def assert_pose_parity(x, x64, tol=1e-5, outlier_frac=0.02):
     """projected poses: norm-wise relative error per pose within the north-star 1e-5 bar (kink poses, see
-    assert_grad_parity, excepted)."""
+    assert_grad_parity, excepted -- bounded by OUTLIER_CAP)."""
     e = per_pose_rel(x, x64)
     assert (e > tol).mean() <= outlier_frac, f"{(e > tol).sum()} of {len(e)} poses above {tol} (max {e.max():.3e})"
+    assert e.max() <= OUTLIER_CAP, f"outlier magnitude {e.max():.3e} above the cap"
     assert np.median(e) < tol / 4

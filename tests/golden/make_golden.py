@@ -60,6 +60,8 @@ CASES = [
 B = 64
 B_TRAIN = 32
 PROJ_STEPS = 10
+PROJ_STEPS_LONG = 50          # BASELINE.json configs[2]: 50-step projection loop
+LONG_CASES = ("lrelu_enc_s1", "softplus_enc_s3")
 
 
 def run_case(PoseNDF, gradient, case):
@@ -90,6 +92,15 @@ def run_case(PoseNDF, gradient, case):
             xp = (xp - (pred["dist_pred"] * gr).reshape(-1, 21, 4)).detach().requires_grad_(True)
         out["proj" + tag] = xp.detach().numpy()
         out["proj_d" + tag] = np.stack(traj_d)
+        if case["name"] in LONG_CASES:
+            # the same loop continued to K = 50 (BASELINE configs[2]); the first 10 steps are the trajectory above
+            for _ in range(PROJ_STEPS, PROJ_STEPS_LONG):
+                pred = net(xp, train=False)
+                traj_d.append(pred["dist_pred"].detach().numpy().copy())
+                gr = gradient(xp, pred["dist_pred"]).reshape(-1, 84)
+                xp = (xp - (pred["dist_pred"] * gr).reshape(-1, 21, 4)).detach().requires_grad_(True)
+            out["proj50_" + tag] = xp.detach().numpy()
+            out["proj50_d" + tag] = np.stack(traj_d)
         if not case["use_enc"]:
             # the reference's train branch raises UnboundLocalError without the encoder
             # (model/posendf.py:81-83 only defines man_pose_in under `if self.enc`), so there is nothing to pin

@@ -65,26 +65,26 @@ def test_train_forward_on_cpu_fails_loudly():
 
 
 def test_train_forward_matches_reference_losses():
-    """the torch-autograd cross-check mode (fused_train=False) that the GPU tests compare the fused train step with:
+    """the torch-autograd cross-check (tests/autograd_crosscheck.py) that the GPU tests compare the native train step with:
     in fp64 on the CPU its values must equal the reference's."""
+    from autograd_crosscheck import train_forward_autograd
     from conftest import load_golden
     meta, z = load_golden("lrelu_enc_s1")
     opt = make_opt()
-    opt["train"]["fused_train"] = False
     net = PoseNDF(opt).double()
     net.load_state_dict({k: torch.from_numpy(v).double() for k, v in synth.make_params(1).items()})
     s = meta["seed"]
     tp = torch.from_numpy(synth.make_poses(2000 + s, 32, kind="noisy", sigma=0.25)).double()
     tm = torch.from_numpy(synth.make_poses(3000 + s, 32, kind="randn")).double()
     tgt = torch.from_numpy((synth.uniform01(4000 + s, 32) * 0.5).astype(np.float32)).double()
-    loss, ld = net(tp, tgt, tm, train=True, eikonal=1.0)
+    loss, ld = train_forward_autograd(net, tp, tgt, tm, 1.0)
     for k in ("dist", "man_loss", "eikonal"):
         assert abs(ld[k].item() - float(z[f"train_{k}64"])) < 1e-12
     sum(ld.values()).backward()
     names = [n for n, _ in synth.param_shapes(126, use_enc=True)]
     norms = np.array([dict(net.named_parameters())[n].grad.norm().item() for n in names])
     assert np.allclose(norms, z["train_gradnorms64"], rtol=1e-9, atol=1e-14)
-    _, ld0 = net(tp, tgt, tm, train=True, eikonal=0.0)
+    _, ld0 = train_forward_autograd(net, tp, tgt, tm, 0.0)
     assert set(ld0) == {"dist"}
 
 
