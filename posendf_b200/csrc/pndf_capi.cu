@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -78,8 +79,11 @@ struct pndf_handle {
     unsigned int* d_loss_counter = nullptr;
     double* d_loss_totals = nullptr;  // [3]
     // denoise loop state (pndf_denoise_prior): raw gradient, Adam moments, dist
-    float* d_dn[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* d_dn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // + second distance buffer
     int64_t dn_poses = 0;
+    cudaStream_t cap_stream = nullptr;   // graph capture of the denoise loop
+    cudaGraphExec_t dn_exec = nullptr;
+    bool in_capture = false;
 };
 
 namespace {
@@ -306,7 +310,7 @@ int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st, int slot = 0) 
     p.enc_beta = h->cfg.enc_beta; p.df_beta = h->cfg.df_beta;
     p.f0_slabs = h->f0_slabs; p.z0_rows = h->z0_rows; p.in_dim = h->cfg.in_dim;
     const int grid = std::min(p.ntiles, h->num_sms);
-    if (order_after_weights(h, st)) return 1;
+    if (!h->in_capture && order_after_weights(h, st)) return 1;
     if (mode == 1)
         pndf_fused_kernel<1><<<grid, kThreads, kSmTotal, st>>>(p);
     else if (mode == 2)
@@ -314,10 +318,11 @@ int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st, int slot = 0) 
     else
         pndf_fused_kernel<0><<<grid, kThreads, kSmTotal, st>>>(p);
     CUDA_OK(cudaGetLastError());
+    h->launches++;
+    if (h->in_capture) return 0;       // events must not be recorded into a capture; the caller records after the graph launch
     CUDA_OK(cudaEventRecord(h->use_event, st));
     h->use_stream = st;
     h->used = true;
-    h->launches++;
     return 0;
 }
 
@@ -373,7 +378,9 @@ int pndf_destroy(pndf_handle* h) {
         cudaFree(h->d_scratch[i]);
         cudaFree(h->d_z0[i]);
     }
-    for (int i = 0; i < 4; ++i) cudaFree(h->d_dn[i]);
+    for (int i = 0; i < 5; ++i) cudaFree(h->d_dn[i]);
+    if (h->dn_exec) cudaGraphExecDestroy(h->dn_exec);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     for (int i = 0; i < 3; ++i) cudaFree(h->d_pos[i]);
     cudaFree(h->d_ws);
     cudaFree(h->d_encrows);
@@ -566,43 +573,85 @@ int pndf_denoise_prior(pndf_handle* h, float* aa_dev, int64_t S, int64_t T, int 
     if (S < 0 || T < 0 || !aa_dev) return fail("null argument");
     if (iterations < 1 || steps_per_iter < 1) return fail("iterations and steps_per_iter must be >= 1");
     if (T > (1 << 24) / 63) return fail("sequence too long");
+    if (!h->have_weights) return fail("pndf_set_weights has not been called");
     CUDA_OK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t B = S * T;
     if (h->dn_poses < B) {
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 5; ++i) {
             cudaFree(h->d_dn[i]);
             h->d_dn[i] = nullptr;
         }
         for (int i = 0; i < 3; ++i) CUDA_OK(cudaMalloc(&h->d_dn[i], (size_t)B * 63 * sizeof(float)));
-        CUDA_OK(cudaMalloc(&h->d_dn[3], (size_t)B * sizeof(float)));
+        for (int i = 3; i < 5; ++i) CUDA_OK(cudaMalloc(&h->d_dn[i], (size_t)B * sizeof(float)));
         h->dn_poses = B;
     }
     float* graw = h->d_dn[0];
     float* m = h->d_dn[1];
     float* v = h->d_dn[2];
-    float* dist = dist_dev ? dist_dev : h->d_dn[3];
-    CUDA_OK(cudaMemsetAsync(m, 0, (size_t)B * 63 * sizeof(float), st));
-    CUDA_OK(cudaMemsetAsync(v, 0, (size_t)B * 63 * sizeof(float), st));
+    // distances are double-buffered (the update prologue of step t reads whole sequences of step t-1 while other CTAs already
+    // write step t); the buffers alternate so that the LAST step lands in the caller's array
+    float* dbuf[2] = {dist_dev ? dist_dev : h->d_dn[3], h->d_dn[4]};
+    const int nsteps = iterations * steps_per_iter;
     const double b1 = 0.9, b2 = 0.999;
-    double p1 = 1.0, p2 = 1.0;
-    int t = 0;
-    for (int it = 0; it < iterations; ++it) {
-        for (int i = 0; i < steps_per_iter; ++i, ++t) {
+    auto adam_of = [&](int t1, int it) {      // parameters of update number t1 (1-based), loss weight of outer iteration `it`
+        AdamParams ap;
+        ap.lr = lr; ap.beta1 = (float)b1; ap.beta2 = (float)b2; ap.eps = 1e-8f;
+        ap.bias1 = (float)(1.0 - std::pow(b1, (double)t1)); ap.bias2 = (float)(1.0 - std::pow(b2, (double)t1));
+        ap.weight = 1e7f / (1.0f + (float)it);
+        return ap;
+    };
+    // ONE launch per optimisation step (prior + gradient, with the previous step's Adam update fused into its prologue) and one
+    // trailing update kernel; the whole loop is captured into a CUDA graph and replayed as a single graph launch
+    auto enqueue = [&](cudaStream_t s) -> int {
+        if (cudaMemsetAsync(m, 0, (size_t)B * 63 * sizeof(float), s) != cudaSuccess) return fail("cudaMemsetAsync failed");
+        if (cudaMemsetAsync(v, 0, (size_t)B * 63 * sizeof(float), s) != cudaSuccess) return fail("cudaMemsetAsync failed");
+        for (int t = 0; t < nsteps; ++t) {
             KParams p{};
-            p.pose_in = aa_dev; p.dist = dist; p.grad = graw; p.B = B; p.steps = 1; p.normalise = 1; p.input_kind = IN_AXIS_ANGLE;
-            if (launch(h, p, 1, st)) return 1;
-            p1 *= b1; p2 *= b2;
-            AdamParams ap;
-            ap.lr = lr; ap.beta1 = (float)b1; ap.beta2 = (float)b2; ap.eps = 1e-8f;
-            ap.bias1 = (float)(1.0 - p1); ap.bias2 = (float)(1.0 - p2);
-            ap.weight = 1e7f / (1.0f + (float)it);
-            seq_adam_kernel<<<(unsigned)S, 256, 0, st>>>(aa_dev, graw, dist, m, v,
-                                                         loss_hist_dev ? loss_hist_dev + (size_t)t * S : nullptr, (int)T, ap);
-            CUDA_OK(cudaGetLastError());
-            h->launches++;
+            p.pose_in = aa_dev; p.dist = dbuf[(nsteps - 1 - t) & 1]; p.grad = graw; p.B = B; p.steps = 1; p.normalise = 1;
+            p.input_kind = IN_AXIS_ANGLE;
+            if (t > 0) {
+                p.dn.pending = 1; p.dn.m = m; p.dn.v = v; p.dn.graw = graw; p.dn.dist_prev = dbuf[(nsteps - t) & 1];
+                p.dn.pose_rw = aa_dev; p.dn.T = (int)T; p.dn.ap = adam_of(t, (t - 1) / steps_per_iter);
+                p.dn.loss_out = loss_hist_dev ? loss_hist_dev + (size_t)(t - 1) * S : nullptr;
+            }
+            if (launch(h, p, 1, s)) return 1;
+        }
+        seq_adam_kernel<<<(unsigned)S, 256, 0, s>>>(aa_dev, graw, dbuf[0], m, v,
+                                                    loss_hist_dev ? loss_hist_dev + (size_t)(nsteps - 1) * S : nullptr, (int)T,
+                                                    adam_of(nsteps, (nsteps - 1) / steps_per_iter));
+        if (cudaGetLastError() != cudaSuccess) return fail("seq_adam_kernel launch failed");
+        h->launches++;
+        return 0;
+    };
+    if (order_after_weights(h, st)) return 1;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    CUDA_OK(cudaStreamIsCapturing(st, &cs));
+    bool graphed = false;
+    if (cs == cudaStreamCaptureStatusNone && !getenv("PNDF_NO_GRAPH")) {
+        // capture on an internal stream (the caller's may be the legacy default stream, which cannot be captured), replay on the caller's
+        if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) h->cap_stream = nullptr;
+        if (h->cap_stream && cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            h->in_capture = true;
+            const int64_t launches0 = h->launches;
+            const int rc = enqueue(h->cap_stream);
+            h->in_capture = false;
+            cudaGraph_t g = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
+            if (rc == 0 && e == cudaSuccess && g) {
+                if (h->dn_exec) { cudaGraphExecDestroy(h->dn_exec); h->dn_exec = nullptr; }
+                if (cudaGraphInstantiate(&h->dn_exec, g, 0) == cudaSuccess && cudaGraphLaunch(h->dn_exec, st) == cudaSuccess) graphed = true;
+            }
+            if (g) cudaGraphDestroy(g);
+            if (!graphed) { cudaGetLastError(); h->launches = launches0; }
+        } else {
+            cudaGetLastError();
         }
     }
+    if (!graphed && enqueue(st)) return 1;
+    CUDA_OK(cudaEventRecord(h->use_event, st));
+    h->use_stream = st;
+    h->used = true;
     return 0;
 }
 
@@ -753,11 +802,12 @@ int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_
     CUDA_OK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n_params = param_count(&h->cfg);
+    const size_t ws_stride = (n_params + 3) & ~(size_t)3;      // 16-byte aligned workspace slots (vector stores)
     const int ksplits = (int)((B + kWgKC - 1) / kWgKC);
     if (h->ws_slots < ksplits) {
         cudaFree(h->d_ws);
         h->d_ws = nullptr;
-        CUDA_OK(cudaMalloc(&h->d_ws, (size_t)ksplits * n_params * sizeof(float)));
+        CUDA_OK(cudaMalloc(&h->d_ws, (size_t)ksplits * ws_stride * sizeof(float)));
         h->ws_slots = ksplits;
     }
     if (!h->d_encrows) CUDA_OK(cudaMalloc(&h->d_encrows, 2 * kEncFloats * sizeof(float)));
@@ -779,7 +829,7 @@ int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_
     const int a_col[6] = {5120, 4608, 3584, 3072, 2816, 2752};
     WgParams p{};
     p.dump = dump_dev; p.dump_t = dump_t_dev; p.coef = coef_dev; p.up = up_dev; p.w_eik = w_eik_dev; p.uniform = uniform;
-    p.ws = h->d_ws; p.B = B; p.n_params = (long long)n_params; p.slot0 = 0; p.nprob = 6;
+    p.ws = h->d_ws; p.B = B; p.ws_stride = (long long)ws_stride; p.slot0 = 0; p.nprob = 6;
     int tiles = 0;
     // big layers first: their CTAs start first inside every K-split
     const int order[6] = {2, 3, 1, 4, 0, 5};
@@ -796,7 +846,7 @@ int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_
     CUDA_OK(cudaGetLastError());
     WgLastParams lp{};
     lp.dump = dump_dev; lp.dump_t = dump_t_dev; lp.coef = coef_dev; lp.up = up_dev; lp.w_eik = w_eik_dev; lp.dist = dist_dev;
-    lp.uniform = uniform; lp.ws = h->d_ws; lp.B = B; lp.n_params = (long long)n_params; lp.w6_off = w_off[6]; lp.b6_off = b_off[6];
+    lp.uniform = uniform; lp.ws = h->d_ws; lp.B = B; lp.ws_stride = (long long)ws_stride; lp.w6_off = w_off[6]; lp.b6_off = b_off[6];
     lp.slot0 = 0; lp.z6_col = z_col[6]; lp.softplus = (h->cfg.df_act == PNDF_ACT_SOFTPLUS); lp.beta = h->cfg.df_beta;
     wgrad_last_kernel<<<(unsigned)ksplits, 256, 0, st>>>(lp);
     CUDA_OK(cudaGetLastError());
@@ -813,7 +863,7 @@ int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_
         n_enc_rows = (ep.weik || ep.upz) ? 2 : 1;
         h->launches++;
     }
-    wgrad_reduce_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, st>>>(h->d_ws, ksplits, (long long)n_params,
+    wgrad_reduce_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, st>>>(h->d_ws, ksplits, (long long)ws_stride, (long long)n_params,
                                                                            h->cfg.use_enc ? kEncFloats : 0, h->d_encrows, n_enc_rows,
                                                                            grad_flat_dev, overwrite);
     CUDA_OK(cudaGetLastError());

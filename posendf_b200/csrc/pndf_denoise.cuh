@@ -11,13 +11,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
-namespace pndf {
+#include "pndf_kernel.cuh"      // AdamParams, dn_adam_update (shared with the update fused into the prior launch)
 
-struct AdamParams {
-    float lr, beta1, beta2, eps;
-    float bias1, bias2;      // 1 - beta^t for this step
-    float weight;            // 1e7 / (1 + it)
-};
+namespace pndf {
 
 __global__ void __launch_bounds__(256) seq_adam_kernel(float* __restrict__ aa, const float* __restrict__ graw,
                                                        const float* __restrict__ dist, float* __restrict__ m,
@@ -43,16 +39,10 @@ __global__ void __launch_bounds__(256) seq_adam_kernel(float* __restrict__ aa, c
     __syncthreads();
     const float scale = s_scale;
     const size_t base = (size_t)s * T * 63;
-    const float step = ap.lr / ap.bias1;
-    const float inv_sqrt_b2 = 1.0f / sqrtf(ap.bias2);
     for (int i = threadIdx.x; i < T * 63; i += blockDim.x) {
-        const float g = scale * graw[base + i];
-        const float mi = ap.beta1 * m[base + i] + (1.0f - ap.beta1) * g;
-        const float vi = ap.beta2 * v[base + i] + (1.0f - ap.beta2) * g * g;
-        m[base + i] = mi;
-        v[base + i] = vi;
-        const float denom = sqrtf(vi) * inv_sqrt_b2 + ap.eps;
-        aa[base + i] -= step * (mi / denom);
+        float av = aa[base + i], mi = m[base + i], vi = v[base + i];
+        dn_adam_update(av, mi, vi, graw[base + i], scale, ap);
+        aa[base + i] = av; m[base + i] = mi; v[base + i] = vi;
     }
 }
 

@@ -65,6 +65,36 @@ constexpr int kDumpRows = 5504;
 enum { ACT_RELU = 0, ACT_LRELU = 1, ACT_SOFTPLUS = 2 };
 enum { IN_QUAT = 0, IN_AXIS_ANGLE = 1 };
 
+// ---- motion-denoise loop (experiments/motion_denoise.py:70-99), fused into the prior launch
+struct AdamParams {
+    float lr, beta1, beta2, eps;
+    float bias1, bias2;      // 1 - beta^t for this step
+    float weight;            // 1e7 / (1 + it)
+};
+// torch.optim.Adam's update of one axis-angle component with gradient g = scale * (raw d dist / d aa), same op order as
+// seq_adam_kernel has always used (pndf_denoise.cuh)
+__device__ __forceinline__ void dn_adam_update(float& a, float& m, float& v, float graw, float scale, const AdamParams& ap) {
+    const float g = scale * graw;
+    m = ap.beta1 * m + (1.0f - ap.beta1) * g;
+    v = ap.beta2 * v + (1.0f - ap.beta2) * g * g;
+    const float denom = sqrtf(v) * (1.0f / sqrtf(ap.bias2)) + ap.eps;
+    a -= (ap.lr / ap.bias1) * (m / denom);
+}
+// One launch per optimisation step: the launch of step t FIRST applies the Adam update that step t-1's gradient asked for
+// (needs mean_t dist of whole sequences -> only known once launch t-1 has finished everywhere; read from dist_prev), then
+// evaluates prior + gradient at the updated poses.  The last update is applied by seq_adam_kernel.
+struct DenoiseFuse {
+    float* m;                 // Adam moments, [B][63]
+    float* v;
+    const float* graw;        // raw gradient of the previous step, [B][63] (this launch overwrites it through KParams::grad)
+    const float* dist_prev;   // distances of the previous step, [S][T]
+    float* loss_out;          // [S] loss of the previous step (weight * mean(dist)^2) or nullptr
+    float* pose_rw;           // the axis-angle poses, updated in place
+    int T;                    // frames per sequence
+    int pending;              // 0: first step, nothing to apply
+    AdamParams ap;            // of the pending update
+};
+
 struct KParams {
     const float* wstream;     // slab stream (forward ops then reverse ops)
     const float* bias[7];     // dfnet.lin{l}.bias
@@ -85,6 +115,7 @@ struct KParams {
     // fused gather (multi-GPU projection runs): the write-back also stores every projected tile -- and its distances --
     // into the gathered buffers of up to kMaxPeers other GPUs through NVLink-mapped (cudaIpc) pointers, each already
     // offset to this rank's slice.  The transfer rides under the FMA work of the following tiles.
+    DenoiseFuse dn;
     float* peer_pose[kMaxPeers];
     float* peer_dist[kMaxPeers];
     int n_peers;
@@ -823,11 +854,47 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             }
         } else {
             const float* src = p.pose_in + pose0 * 63;
+            const bool dn = (p.dn.pending != 0);
+            if (dn) {
+                // per-sequence loss scale of the PREVIOUS step for every sequence that has a frame in this tile:
+                // c = mean_t dist_prev[s][t] (same summation order as seq_adam_kernel), scale = weight * 2 c / T
+                const int T = p.dn.T;
+                const long long s_lo = pose0 / T, s_hi = (pose0 + nvalid - 1) / T;
+                for (long long sq = s_lo; sq <= s_hi; ++sq) {
+                    const float* dp = p.dn.dist_prev + sq * T;
+                    float acc = 0.0f;
+                    for (int t = tid; t < T; t += kGemmThreads) acc += dp[t];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) nrm[warp] = acc;
+                    __syncthreads();
+                    if (tid == 0) {
+                        float tot = 0.0f;
+                        for (int w = 0; w < kWarps; ++w) tot += nrm[w];
+                        const float cmean = tot / (float)T;
+                        dval[sq - s_lo] = p.dn.ap.weight * 2.0f * cmean / (float)T;
+                        if (p.dn.loss_out != nullptr && sq * T >= pose0) p.dn.loss_out[sq] = p.dn.ap.weight * cmean * cmean;
+                    }
+                    __syncthreads();
+                }
+            }
             for (int idx = tid; idx < kTileM * 21; idx += kGemmThreads) {
                 const int m = idx / 21, j = idx - m * 21;
                 float a[3] = {0.f, 0.f, 0.f}, q[4];
                 if (m < nvalid) {
-                    a[0] = __ldg(src + idx * 3); a[1] = __ldg(src + idx * 3 + 1); a[2] = __ldg(src + idx * 3 + 2);
+                    if (dn) {
+                        const long long e0 = (pose0 * 21 + idx) * 3;
+                        const float scale = dval[(pose0 + m) / p.dn.T - pose0 / p.dn.T];
+#pragma unroll
+                        for (int k3 = 0; k3 < 3; ++k3) {
+                            float av = p.dn.pose_rw[e0 + k3], mv = p.dn.m[e0 + k3], vv = p.dn.v[e0 + k3];
+                            dn_adam_update(av, mv, vv, p.dn.graw[e0 + k3], scale, p.dn.ap);
+                            p.dn.pose_rw[e0 + k3] = av; p.dn.m[e0 + k3] = mv; p.dn.v[e0 + k3] = vv;
+                            a[k3] = av;
+                        }
+                    } else {
+                        a[0] = __ldg(src + idx * 3); a[1] = __ldg(src + idx * 3 + 1); a[2] = __ldg(src + idx * 3 + 2);
+                    }
                 }
                 aa_to_quat(a, q);
 #pragma unroll
@@ -1102,7 +1169,8 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                     float* dst = p.grad + pose0 * 63;
                     for (int idx = tid; idx < nvalid * 21; idx += kGemmThreads) {
                         const int m = idx / 21, j = idx - m * 21;
-                        const float a[3] = {__ldg(src + idx * 3), __ldg(src + idx * 3 + 1), __ldg(src + idx * 3 + 2)};
+                        // plain loads: in the fused denoise step this CTA has just rewritten these values (prologue)
+                        const float a[3] = {src[idx * 3], src[idx * 3 + 1], src[idx * 3 + 2]};
                         const float qb[4] = {Y[swz(128 + j * 4, m)], Y[swz(128 + j * 4 + 1, m)], Y[swz(128 + j * 4 + 2, m)],
                                              Y[swz(128 + j * 4 + 3, m)]};
                         float ab[3];

@@ -49,7 +49,7 @@ struct WgParams {
     const float* w_eik;      // device scalar: upstream gradient of the Eikonal loss (used with dump_t) or nullptr
     float uniform;
     float* ws;               // workspace [slot][n_params]
-    long long B, n_params;
+    long long B, ws_stride;  // ws_stride = n_params rounded up to a multiple of 4 floats (16-byte aligned slots)
     int slot0;               // this batch's first workspace slot; slot = slot0 + blockIdx.y
     int nprob;
     WgProblem prob[kWgMaxProblems];
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(const WgParams p) 
 
     // ---- partial tile -> workspace slot (flat parameter layout)
     const float scale = per_pose ? 1.0f : up * p.uniform;
-    float* ws = p.ws + (size_t)(p.slot0 + blockIdx.y) * (size_t)p.n_params;
+    float* ws = p.ws + (size_t)(p.slot0 + blockIdx.y) * (size_t)p.ws_stride;
     float* W = ws + pr.w_off;
     const bool vec = (pr.n_in & 3) == 0;
 #pragma unroll
@@ -234,7 +234,7 @@ struct WgLastParams {
     const float* dist;       // [B]
     float uniform;
     float* ws;
-    long long B, n_params, w6_off, b6_off;
+    long long B, ws_stride, w6_off, b6_off;
     int slot0, z6_col, softplus;
     float beta;
 };
@@ -258,14 +258,15 @@ __global__ void __launch_bounds__(256) wgrad_last_kernel(const WgLastParams p) {
     part[kq][n] = acc;
     if (n == 0) part[kq][64] = bacc;
     __syncthreads();
-    float* ws = p.ws + (size_t)(p.slot0 + blockIdx.x) * (size_t)p.n_params;
+    float* ws = p.ws + (size_t)(p.slot0 + blockIdx.x) * (size_t)p.ws_stride;
     if (threadIdx.x < 64) ws[p.w6_off + threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
     if (threadIdx.x == 64) ws[p.b6_off] = (part[0][64] + part[1][64]) + (part[2][64] + part[3][64]);
 }
 
 // grad[i] += sum over slots of ws[slot][i] (fixed order) for the DFNet part i >= enc_floats, and the encoder kernel's
 // (n_enc_rows x enc_floats) block accumulators for i < enc_floats.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int nslots, long long n_params, int enc_floats,
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int nslots, long long ws_stride, long long n_params,
+                                                           int enc_floats,
                                                            const float* __restrict__ enc_rows, int n_enc_rows,
                                                            float* __restrict__ grad, int overwrite) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     if (i < enc_floats) {
         for (int r = 0; r < n_enc_rows; ++r) s += enc_rows[(size_t)r * enc_floats + i];
     } else {
-        for (int k = 0; k < nslots; ++k) s += ws[(size_t)k * n_params + i];
+        for (int k = 0; k < nslots; ++k) s += ws[(size_t)k * ws_stride + i];
     }
     grad[i] = overwrite ? s : grad[i] + s;
 }

@@ -384,3 +384,36 @@ def test_api_misuse_fails_loudly():
     # fp64 / non-contiguous inputs of the out-of-place entry points are converted, not rejected
     d = eng.forward(torch.zeros(8, 21, 4, device="cuda", dtype=torch.float64)[::2] + 0.1)
     assert d.shape == (4, 1) and torch.isfinite(d).all()
+
+
+@pytest.mark.parametrize("S,T", [(3, 40), (70, 1), (5, 7), (2, 300)])
+def test_denoise_one_launch_per_step_graph_equals_plain_launches(S, T, monkeypatch):
+    """f1: steps + 1 launches (the Adam update of step t-1 rides in the prologue of launch t), replayed as one CUDA graph;
+    the graph replay and plain launches give identical bits, also when a tile holds many short sequences (T = 1, 7) or a
+    sequence spans many tiles (T = 300), and the result follows the fp64 oracle."""
+    meta, _ = load_golden("softplus_enc_s3")       # smooth network: no kink flips between fp32 and the fp64 oracle
+    cfg = case_cfg(meta)
+    params, _ = case_inputs(meta)
+    eng = make_engine(meta, params)
+    aa = synth.make_axis_angle(21, S * T).reshape(S, T, 21, 3)
+    outs = []
+    for no_graph in (False, True):
+        if no_graph:
+            monkeypatch.setenv("PNDF_NO_GRAPH", "1")
+        else:
+            monkeypatch.delenv("PNDF_NO_GRAPH", raising=False)
+        x = torch.from_numpy(aa).cuda().contiguous()
+        n0 = eng.launch_count()
+        d, hist = eng.denoise_prior_(x, iterations=2, steps_per_iter=3, lr=0.02, want_loss=True)
+        torch.cuda.synchronize()
+        assert eng.launch_count() - n0 == 2 * 3 + 1
+        outs.append((x.clone(), d.clone(), hist.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    xref, dref, href = onp.denoise_prior(p64, aa.astype(np.float64), cfg, iterations=2, steps_per_iter=3)
+    x, d, hist = (t.cpu().numpy() for t in outs[0])
+    assert np.max(np.abs(hist - href) / np.abs(href)) < 2e-5
+    assert np.max(rel_err(d, dref)) < 1e-5
+    err = np.abs(x - xref)
+    assert np.median(err) < 2e-6 and (err > 1e-4).mean() < 0.01, (np.median(err), err.max())

@@ -194,12 +194,18 @@ def test_dead_poses_zero_gradient_norm_stay_finite_and_match_autograd():
     agree with the reference's autograd (fp64 oracle) -- the Eikonal tangent kernel masks |g| == 0."""
     from posendf_b200 import PoseNDF
     cfg = dict(use_enc=True, enc_act="lrelu", enc_beta=100.0, df_act="lrelu", df_beta=100.0)
-    params = synth.make_params(0, sensitised=False)          # seed 0: d == 0 everywhere (SURVEY Appx D)
+    params = synth.make_params(1)
     net = PoseNDF(_opt(cfg))
     net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
     tp, tgt, tm = _batch(0, 96)
+    # shift the output bias so that the last pre-activation straddles zero: about half of the poses get d == 0 (ReLU output)
+    # and with it an all-zero pose gradient -- what default-init weights or near-manifold poses of a trained net produce
+    d0 = net(torch.from_numpy(tp), train=False)["dist_pred"]
+    params["dfnet.lin6.bias"] = (params["dfnet.lin6.bias"] - np.float32(d0.median().item())).astype(np.float32)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    dead = (net(torch.from_numpy(tp), train=False)["dist_pred"] == 0).float().mean().item()
+    assert 0.2 < dead < 0.8
     _, ld = net(torch.from_numpy(tp), torch.from_numpy(tgt), torch.from_numpy(tm), train=True, eikonal=1.0)
-    assert (net(torch.from_numpy(tp), train=False)["dist_pred"] == 0).float().mean().item() > 0.5
     sum(ld.values()).backward()
     tp64 = otorch.to_torch_params(params, torch.float64, requires_grad=True)
     _, ld_ref, g_ref = otorch.train_step_grads(tp64, torch.from_numpy(tp).double(), torch.from_numpy(tgt).double(),
