@@ -18,6 +18,14 @@
 
 using namespace pndf;
 
+namespace pndf {
+using FusedFn = void (*)(const KParams);
+FusedFn pndf_fused_entry_00(int mode);
+FusedFn pndf_fused_entry_01(int mode);
+FusedFn pndf_fused_entry_10(int mode);
+FusedFn pndf_fused_entry_11(int mode);
+}  // namespace pndf
+
 namespace {
 
 thread_local std::string g_err;
@@ -289,6 +297,13 @@ __global__ void peer_barrier_kernel(PeerFlags f, int world, int rank, uint32_t e
     }
 }
 
+// the 12 instances of the fused kernel (MODE x softplus DFNet x softplus encoder) live in four translation units
+// (pndf_fused_inst.cu, compiled in parallel)
+FusedFn fused_fn(int mode, bool dsoft, bool esoft) {
+    if (dsoft) return esoft ? pndf_fused_entry_11(mode) : pndf_fused_entry_10(mode);
+    return esoft ? pndf_fused_entry_01(mode) : pndf_fused_entry_00(mode);
+}
+
 int ensure_slot(pndf_handle* h, int slot) {
     if (!h->d_z0[slot]) CUDA_OK(cudaMalloc(&h->d_z0[slot], (size_t)h->num_sms * 128 * 32 * sizeof(float)));
     if (h->cfg.df_act == PNDF_ACT_SOFTPLUS && !h->d_scratch[slot])
@@ -311,12 +326,7 @@ int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st, int slot = 0) 
     p.f0_slabs = h->f0_slabs; p.z0_rows = h->z0_rows; p.in_dim = h->cfg.in_dim;
     const int grid = std::min(p.ntiles, h->num_sms);
     if (!h->in_capture && order_after_weights(h, st)) return 1;
-    if (mode == 1)
-        pndf_fused_kernel<1><<<grid, kThreads, kSmTotal, st>>>(p);
-    else if (mode == 2)
-        pndf_fused_kernel<2><<<grid, kThreads, kSmTotal, st>>>(p);
-    else
-        pndf_fused_kernel<0><<<grid, kThreads, kSmTotal, st>>>(p);
+    fused_fn(mode, h->cfg.df_act == PNDF_ACT_SOFTPLUS, h->cfg.enc_act == PNDF_ACT_SOFTPLUS)<<<grid, kThreads, kSmTotal, st>>>(p);
     CUDA_OK(cudaGetLastError());
     h->launches++;
     if (h->in_capture) return 0;       // events must not be recorded into a capture; the caller records after the graph launch
@@ -354,9 +364,9 @@ int pndf_create(const pndf_config* cfg, pndf_handle** out) {
     h->num_sms = prop.multiProcessorCount;
     h->z0_rows = cfg->use_enc ? 128 : 96;
     h->f0_slabs = slabs_of(h->z0_rows, 2, 64);
-    CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
-    CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
-    CUDA_OK(cudaFuncSetAttribute(pndf_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
+    for (int mode = 0; mode < 3; ++mode)
+        CUDA_OK(cudaFuncSetAttribute(fused_fn(mode, cfg->df_act == PNDF_ACT_SOFTPLUS, cfg->enc_act == PNDF_ACT_SOFTPLUS),
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
     if (ensure_slot(h, 0)) { pndf_destroy(h); return 1; }
     if (cudaEventCreateWithFlags(&h->use_event, cudaEventDisableTiming) != cudaSuccess) { pndf_destroy(h); return fail("cudaEventCreate failed"); }
     if (build_maps(h)) { pndf_destroy(h); return 1; }

@@ -37,7 +37,7 @@ constexpr int kStages = 2;            // per-warp stages
 constexpr int kWarps = 8;
 // per-warp slab count of an op with K reduction rows split over KG K-groups and FW columns per warp
 __host__ __device__ constexpr int slabs_of(int K, int KG, int FW) { return (K / KG) * FW / kSlabFloats; }
-constexpr int kXS = 85;               // padded row stride of the pose tile
+constexpr int kXS = 84;               // row stride of the pose tile: the tile is a plain image of 32 x 336 bytes of the batch (bulk copies)
 constexpr int kMaskStride = 2656;     // bytes per pose-group plane of the derivative bit masks
 constexpr int kUnits = 2624;          // hidden units of the DFNet (256+512+1024+512+256+64)
 constexpr int kEncFloats = 3516;
@@ -157,6 +157,21 @@ __device__ __forceinline__ float softplus_eval(float v, float beta, float inv_be
     deriv = lin ? 1.0f : e * r;
     return lin ? v : log1pf(e) * inv_beta;
 }
+// The same on the SFU (the GEMM epilogues evaluate it 84 000 times per 32-pose tile): e = 2^(bx log2 e) (ex2.approx, 2 ulp),
+// sigma = e / (1 + e) through rcp.approx (1 ulp), log1p(e) = ln2 * lg2(1 + e) (lg2.approx: absolute error < 2^-22 near 1, i.e.
+// < 2e-7 ln2 / beta on the activation).  Validated against the reference's fp64 goldens at the 1e-5 bar for beta = 5, 30,
+// 100 (tests/test_gpu_parity.py); the exact version above stays in use for the scalar output unit and the encoder.
+__device__ __forceinline__ float softplus_fast(float v, float beta, float inv_beta_ln2, float& deriv) {
+    const float bx = v * beta;
+    const bool lin = bx > 20.0f;
+    float e, r, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(bx, 20.0f) * 1.4426950408889634f));
+    const float u = 1.0f + e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(u));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));
+    deriv = lin ? 1.0f : e * r;
+    return lin ? v : l * inv_beta_ln2;
+}
 
 __device__ __forceinline__ float act_eval(float v, int kind, float beta, float& deriv) {
     if (kind == ACT_SOFTPLUS) return softplus_eval(v, beta, 1.0f / beta, deriv);
@@ -199,8 +214,8 @@ struct Ctx {
     float* dscr;   // this CTA's derivative scratch (softplus) or nullptr
     int tid, lane, mg, ng;
     int ng2, kg;   // split-K ops (N = 256): feature group within a 4-warp K-group, and the K-group (0/1)
-    int df_act;
-    float df_beta, df_inv_beta;
+    float slope;                       // relu 0 / lrelu 0.01 (piecewise-linear DFNet activation)
+    float df_beta, df_inv_beta_ln2;    // softplus DFNet: beta, ln2 / beta
 };
 
 // KG = number of K-groups an op is split into: KG == 1, all 8 warps tile N = 64*TN features; KG == 2 (split-K, used for
@@ -253,6 +268,15 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait_s(bar, parity)) {
         if (++spins > (1u << 26)) __trap();
     }
+}
+// 1-D bulk copies (TMA) global -> shared completing on an mbarrier, shared -> global in a bulk group
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
 // The warp has finished reading ring slot `stage` (caller did __syncwarp): refill it with the warp's next slab.
 __device__ __forceinline__ void refill(Pipe& pipe, const Ctx& c, uint32_t stage) {
@@ -428,17 +452,17 @@ __device__ __forceinline__ void mask_load(const uint8_t* mask, int mg, int unit0
 
 // forward epilogue: z = act(acc) (bias already in acc), remember the derivative, store z as next input.
 // unit_base: index of feature 0 of this op in the mask / scratch unit space.
-template <int TN, int KG = 1>
+template <bool SOFT, int TN, int KG = 1>
 __device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* out, int unit_base, const Ctx& c, bool keep_deriv) {
     const int ng = ngv<KG>(c);
     const int unit0 = unit_base + feat_of<TN, KG>(ng, 0);
-    if (c.df_act == ACT_SOFTPLUS) {
+    if (SOFT) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             const int f = feat_of<TN, KG>(ng, j);
             float z[8], dv[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) z[i] = softplus_eval(acc[i][j], c.df_beta, c.df_inv_beta, dv[i]);
+            for (int i = 0; i < 8; ++i) z[i] = softplus_fast(acc[i][j], c.df_beta, c.df_inv_beta_ln2, dv[i]);
             store_row8(out, f, c.mg, z);
             if (keep_deriv) {
                 float* p = c.dscr + (size_t)(unit_base + f) * 32 + c.mg * 8;
@@ -447,7 +471,7 @@ __device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* o
             }
         }
     } else {
-        const float slope = (c.df_act == ACT_RELU) ? 0.0f : 0.01f;
+        const float slope = c.slope;
         uint32_t bits[TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
@@ -470,7 +494,7 @@ __device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* o
 
 // reverse epilogue: g = acc * act'(pre) of the layer whose input-gradient this op produced; store as the
 // next reverse op's input.  unit_base < 0: no derivative (the encoder features, handled by the encoder).
-template <int TN, int KG = 1>
+template <bool SOFT, int TN, int KG = 1>
 __device__ __forceinline__ void epilogue_bwd(const float (&acc)[8][TN], float* out, int unit_base, const Ctx& c) {
     const int ng = ngv<KG>(c);
     if (unit_base < 0) {
@@ -483,7 +507,7 @@ __device__ __forceinline__ void epilogue_bwd(const float (&acc)[8][TN], float* o
         }
         return;
     }
-    if (c.df_act == ACT_SOFTPLUS) {
+    if (SOFT) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             const int f = feat_of<TN, KG>(ng, j);
@@ -497,7 +521,7 @@ __device__ __forceinline__ void epilogue_bwd(const float (&acc)[8][TN], float* o
             store_row8(out, f, c.mg, v);
         }
     } else {
-        const float slope = (c.df_act == ACT_RELU) ? 0.0f : 0.01f;
+        const float slope = c.slope;
         uint32_t bits[TN];
         mask_load<TN, KG>(c.mask, c.mg, unit_base + feat_of<TN, KG>(ng, 0), bits);
 #pragma unroll
@@ -562,10 +586,10 @@ __device__ __forceinline__ void dump_rows(float* dbg, int row0, const float* buf
 }
 
 // ------------------------------------------------------------------------------------------------ encoder
-__constant__ int c_parent[21] = {-1, -1, -1, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19};
+static __constant__ int c_parent[21] = {-1, -1, -1, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19};
 // non-root joint pairs of the encoder schedule (two independent sub-trees per step), after (1,0) and (3,2)
-__constant__ int c_pair_a[7] = {5, 7, 9, 12, 14, 16, 17};
-__constant__ int c_pair_b[7] = {4, 6, 8, 10, 11, 13, 15};
+static __constant__ int c_pair_a[7] = {5, 7, 9, 12, 14, 16, 17};
+static __constant__ int c_pair_b[7] = {4, 6, 8, 10, 11, 13, 15};
 
 __device__ __forceinline__ int enc_off(int i) { return (i < 3) ? i * 116 : 348 + (i - 3) * 176; }
 
@@ -631,8 +655,8 @@ __device__ __forceinline__ void enc_fwd_pair(const float* encw, const float* qs,
         feat[swz(ia * 6 + e.l, e.m)] = fa;
         feat[swz(ib * 6 + e.l, e.m)] = fb;
         if (stash != nullptr) {
-            stash[(ia * 6 + e.l) * 32 + e.m] = fa;
-            stash[(ib * 6 + e.l) * 32 + e.m] = fb;
+            stash[swz(ia * 6 + e.l, e.m)] = fa;     // same (swizzled) image as rows [0, 126) of the activation buffer:
+            stash[swz(ib * 6 + e.l, e.m)] = fb;     // the reverse pass brings it back with ONE bulk copy
         }
     }
     __syncwarp();
@@ -644,7 +668,7 @@ __device__ __forceinline__ void enc_fwd_one(const float* encw, const float* qs, 
     bone_forward<SOFT, false>(encw + enc_off(i), qs, feat, i, c_parent[i], e, apar, u, h, f, x, y, z);
     if (e.l < 6) {
         feat[swz(i * 6 + e.l, e.m)] = f;
-        if (stash != nullptr) stash[(i * 6 + e.l) * 32 + e.m] = f;
+        if (stash != nullptr) stash[swz(i * 6 + e.l, e.m)] = f;
     }
     __syncwarp();
 }
@@ -770,7 +794,9 @@ __device__ __forceinline__ void aa_to_quat_vjp(const float (&a)[3], const float 
 // MODE 0: forward only.  MODE 1: forward + reverse (+ step).  MODE 2: forward, then the forward-mode tangent of the
 // DFNet along a given input tangent (same weights, activation replaced by a multiply with the stored derivative) --
 // the second launch of a training step (Eikonal term), see posendf_b200/train.py.
-template <int MODE>
+// DSOFT / ESOFT: softplus DFNet / encoder (else piecewise-linear, slope from the config) -- compile-time, so every activation
+// combination is its own kernel without the other variant's code in its epilogues.
+template <int MODE, bool DSOFT, bool ESOFT>
 __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p) {
     constexpr bool kGrad = (MODE == 1);
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -791,6 +817,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
 
     if (tid == 0) {
         for (int i = 0; i < kWarps * kStages; ++i) mbar_init(&full[i], 1);
+        mbar_init(&full[kWarps * kStages], 1);     // aux: pose tile / encoder weights / feature stash bulk copies
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -814,8 +841,11 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     c.ring_s = smem_u32(c.ring); c.full_s = smem_u32(full + warp * kStages);
     c.tid = tid; c.lane = lane; c.mg = lane >> 3; c.ng = warp * 8 + (lane & 7);
     c.ng2 = (warp & 3) * 8 + (lane & 7); c.kg = warp >> 2;
-    c.df_act = p.df_act; c.df_beta = p.df_beta; c.df_inv_beta = 1.0f / p.df_beta;
+    c.slope = (p.df_act == ACT_RELU) ? 0.0f : 0.01f; c.df_beta = p.df_beta; c.df_inv_beta_ln2 = 0.6931471805599453f / p.df_beta;
     c.dscr = p.dscratch ? p.dscratch + (size_t)blockIdx.x * kUnits * 32 : nullptr;
+    const uint32_t aux_s = smem_u32(full + kWarps * kStages);
+    uint32_t aux_phase = 0;
+    constexpr uint32_t kEncBytes = kEncFloats * 4;     // 14 064, a multiple of 16
     const bool keep = (MODE >= 1);
     EncLane enc;
     enc.l = lane & 7; enc.base = lane & 24; enc.m = warp * 4 + (lane >> 3);
@@ -840,18 +870,23 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
 
         // ---- load the pose tile (coalesced), zero-fill the tail
         if (tan_only) {
-            if (p.df_act == ACT_SOFTPLUS) {
+            if (DSOFT) {
                 c.dscr = reinterpret_cast<float*>(p.act_masks) + (size_t)tile * kUnits * 32;
             } else {
                 const uint4* src = reinterpret_cast<const uint4*>(p.act_masks + (size_t)tile * (4 * kMaskStride));
                 for (int i = tid; i < 4 * kMaskStride / 16; i += kGemmThreads) reinterpret_cast<uint4*>(mask)[i] = __ldg(src + i);
             }
         } else if (p.input_kind == IN_QUAT) {
-            const float* src = p.pose_in + pose0 * 84;
-            for (int idx = tid; idx < kTileM * 84; idx += kGemmThreads) {
-                const int m = idx / 84, e = idx - m * 84;
-                xs[m * kXS + e] = (m < nvalid) ? __ldg(src + idx) : 0.0f;
+            // ONE bulk copy: the tile is nvalid x 336 contiguous bytes of the batch; the encoder weights ride on the same barrier
+            if (tid == 0) {
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous tile's write-back has read xs
+                mbar_expect_tx_s(aux_s, (uint32_t)nvalid * 336u + (p.use_enc ? kEncBytes : 0u));
+                bulk_g2s(xs, p.pose_in + pose0 * 84, (uint32_t)nvalid * 336u, aux_s);
+                if (p.use_enc) bulk_g2s(encw, p.encw, kEncBytes, aux_s);
             }
+            for (int idx = nvalid * 84 + tid; idx < kTileM * 84; idx += kGemmThreads) xs[idx] = 0.0f;      // ragged last tile
+            mbar_wait_s(aux_s, aux_phase);
+            aux_phase ^= 1u;
         } else {
             const float* src = p.pose_in + pose0 * 63;
             const bool dn = (p.dn.pending != 0);
@@ -901,7 +936,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 for (int cpt = 0; cpt < 4; ++cpt) xs[m * kXS + j * 4 + cpt] = (m < nvalid) ? q[cpt] : 0.0f;
             }
         }
-        if (p.use_enc && !tan_only) {
+        if (p.use_enc && !tan_only && p.input_kind != IN_QUAT) {
             for (int i = tid; i < kEncFloats; i += kGemmThreads) encw[i] = __ldg(p.encw + i);
         }
         gemm_bar();
@@ -927,9 +962,10 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 __syncwarp();
                 if (p.use_enc) {
                     float* stash = (kGrad && p.z0scratch != nullptr) ? p.z0scratch + (size_t)blockIdx.x * 128 * 32 : nullptr;
-                    if (p.enc_act == ACT_SOFTPLUS) encoder_forward<true>(encw, qs, X, stash, enc, p.enc_beta);
-                    else encoder_forward<false>(encw, qs, X, stash, enc, (p.enc_act == ACT_RELU) ? 0.0f : 0.01f);
+                    encoder_forward<ESOFT>(encw, qs, X, stash, enc, ESOFT ? p.enc_beta : ((p.enc_act == ACT_RELU) ? 0.0f : 0.01f));
                     if (enc.l < 2) X[swz(126 + enc.l, enc.m)] = 0.0f;
+                    // the feature stash (global, written above by this thread) comes back through a bulk copy = async proxy
+                    if (kGrad) asm volatile("fence.proxy.async;" ::: "memory");
                 } else {
                     for (int e = enc.l; e < 96; e += 8) X[swz(e, enc.m)] = (e < 84) ? qs[enc.m * kXS + e] : 0.0f;
                 }
@@ -951,7 +987,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 if (c.kg == 0 && !tangent) acc_init_bias<8, 2>(acc, p.bias[0], c.ng2, 256); else acc_zero<8>(acc);
                 gemm_op<8, 2>(acc, X, p.f0_slabs, pipe, c);
                 splitk_combine<8>(acc, Y, c);
-                if (c.kg == 0) { if (!tangent) epilogue_fwd<8, 2>(acc, Y, kU1, c, keep); else epilogue_bwd<8, 2>(acc, Y, kU1, c); }
+                if (c.kg == 0) { if (!tangent) epilogue_fwd<DSOFT, 8, 2>(acc, Y, kU1, c, keep); else epilogue_bwd<DSOFT, 8, 2>(acc, Y, kU1, c); }
             }
             gemm_bar();
             dump_rows(dbg_p, 128, Y, 256, tid);
@@ -959,7 +995,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 float acc[8][8];
                 if (!tangent) acc_init_bias<8>(acc, p.bias[1], c.ng, 512); else acc_zero<8>(acc);
                 gemm_op<8>(acc, Y, kS1, pipe, c);
-                if (!tangent) epilogue_fwd<8>(acc, X, kU2, c, keep); else epilogue_bwd<8>(acc, X, kU2, c);
+                if (!tangent) epilogue_fwd<DSOFT, 8>(acc, X, kU2, c, keep); else epilogue_bwd<DSOFT, 8>(acc, X, kU2, c);
             }
             gemm_bar();
             dump_rows(dbg_p, 384, X, 512, tid);
@@ -970,13 +1006,13 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                     float acc2[8][8];
                     if (!tangent) acc_init_bias<8>(acc2, p.bias[2] + ch * 512, c.ng, 512); else acc_zero<8>(acc2);
                     gemm_op<8>(acc2, X, kS23, pipe, c);
-                    if (!tangent) epilogue_fwd<8>(acc2, Y, kU3 + ch * 512, c, keep); else epilogue_bwd<8>(acc2, Y, kU3 + ch * 512, c);
+                    if (!tangent) epilogue_fwd<DSOFT, 8>(acc2, Y, kU3 + ch * 512, c, keep); else epilogue_bwd<DSOFT, 8>(acc2, Y, kU3 + ch * 512, c);
                     gemm_bar();
                     dump_rows(dbg_p, 896 + ch * 512, Y, 512, tid);
                     gemm_op<8>(acc3, Y, kS23, pipe, c);
                     gemm_bar();
                 }
-                if (!tangent) epilogue_fwd<8>(acc3, X, kU4, c, keep); else epilogue_bwd<8>(acc3, X, kU4, c);
+                if (!tangent) epilogue_fwd<DSOFT, 8>(acc3, X, kU4, c, keep); else epilogue_bwd<DSOFT, 8>(acc3, X, kU4, c);
             }
             gemm_bar();
             dump_rows(dbg_p, 1920, X, 512, tid);
@@ -985,7 +1021,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 if (c.kg == 0 && !tangent) acc_init_bias<8, 2>(acc, p.bias[4], c.ng2, 256); else acc_zero<8>(acc);
                 gemm_op<8, 2>(acc, X, kS4, pipe, c);
                 splitk_combine<8>(acc, Y, c);
-                if (c.kg == 0) { if (!tangent) epilogue_fwd<8, 2>(acc, Y, kU5, c, keep); else epilogue_bwd<8, 2>(acc, Y, kU5, c); }
+                if (c.kg == 0) { if (!tangent) epilogue_fwd<DSOFT, 8, 2>(acc, Y, kU5, c, keep); else epilogue_bwd<DSOFT, 8, 2>(acc, Y, kU5, c); }
             }
             gemm_bar();
             dump_rows(dbg_p, 2432, Y, 256, tid);
@@ -993,7 +1029,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 float acc[8][1];
                 if (!tangent) acc_init_bias<1>(acc, p.bias[5], c.ng, 64); else acc_zero<1>(acc);
                 gemm_op<1>(acc, Y, kS5, pipe, c);
-                if (!tangent) epilogue_fwd<1>(acc, X, kU6, c, keep); else epilogue_bwd<1>(acc, X, kU6, c);
+                if (!tangent) epilogue_fwd<DSOFT, 1>(acc, X, kU6, c, keep); else epilogue_bwd<DSOFT, 1>(acc, X, kU6, c);
             }
             gemm_bar();
             dump_rows(dbg_p, 2688, X, 64, tid);
@@ -1009,7 +1045,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 s += __ldg(p.bias[6]);
                 if (enc.l == 0) {
                     float dv;
-                    const float d = act_eval(s, (p.df_act == ACT_SOFTPLUS) ? ACT_SOFTPLUS : ACT_RELU, p.df_beta, dv);
+                    const float d = act_eval(s, DSOFT ? ACT_SOFTPLUS : ACT_RELU, p.df_beta, dv);
                     dval[m] = d;
                     float gu = 1.0f;
                     if (p.g_up != nullptr && m < nvalid) gu = __ldg(p.g_up + pose0 + m);
@@ -1024,7 +1060,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             if (MODE == 2) gemm_bar();   // X (z6 / its tangent) is reloaded by the next pass
             }  // passes
             if (MODE == 1 && p.act_masks != nullptr && st == 0) {   // hand the activation derivatives to the tangent launch
-                if (p.df_act == ACT_SOFTPLUS) {   // fp32 derivatives: L2-resident per-CTA scratch -> per-tile buffer, streaming stores
+                if (DSOFT) {   // fp32 derivatives: L2-resident per-CTA scratch -> per-tile buffer, streaming stores
                     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.act_masks) + (size_t)tile * kUnits * 32);
                     const float4* src = reinterpret_cast<const float4*>(c.dscr);
                     for (int i = tid; i < kUnits * 32 / 4; i += kGemmThreads) __stcs(dst + i, src[i]);
@@ -1044,11 +1080,11 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             for (int idx = tid; idx < 64 * 32; idx += kGemmThreads) {
                 const int k = idx >> 5, m = idx & 31;
                 float dv;
-                if (p.df_act == ACT_SOFTPLUS) {
+                if (DSOFT) {
                     dv = c.dscr[(size_t)(kU6 + k) * 32 + m];
                 } else {
                     const uint32_t b = mask[(m >> 3) * kMaskStride + kU6 + k];
-                    dv = ((b >> (m & 7)) & 1u) ? 1.0f : ((p.df_act == ACT_RELU) ? 0.0f : 0.01f);
+                    dv = ((b >> (m & 7)) & 1u) ? 1.0f : c.slope;
                 }
                 Y[swz(k, m)] = dval[32 + m] * __ldg(p.w6 + k) * dv;
             }
@@ -1059,7 +1095,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 acc_zero<8>(acc);
                 gemm_op<8, 2>(acc, Y, kSB5, pipe, c);
                 splitk_combine<8>(acc, X, c);
-                if (c.kg == 0) epilogue_bwd<8, 2>(acc, X, kU5, c);
+                if (c.kg == 0) epilogue_bwd<DSOFT, 8, 2>(acc, X, kU5, c);
             }
             gemm_bar();
             dump_rows(dbg_s, 2816, X, 256, tid);
@@ -1067,7 +1103,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 float acc[8][8];
                 acc_zero<8>(acc);
                 gemm_op<8>(acc, X, kS1, pipe, c);
-                epilogue_bwd<8>(acc, Y, kU4, c);
+                epilogue_bwd<DSOFT, 8>(acc, Y, kU4, c);
             }
             gemm_bar();
             dump_rows(dbg_s, 3072, Y, 512, tid);
@@ -1078,22 +1114,28 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                     float accb3[8][8];
                     acc_zero<8>(accb3);
                     gemm_op<8>(accb3, Y, kS23, pipe, c);
-                    epilogue_bwd<8>(accb3, X, kU3 + ch * 512, c);
+                    epilogue_bwd<DSOFT, 8>(accb3, X, kU3 + ch * 512, c);
                     gemm_bar();
                     dump_rows(dbg_s, 3584 + ch * 512, X, 512, tid);
                     gemm_op<8>(accb2, X, kS23, pipe, c);
                     gemm_bar();
                 }
-                epilogue_bwd<8>(accb2, Y, kU2, c);
+                epilogue_bwd<DSOFT, 8>(accb2, Y, kU2, c);
             }
             gemm_bar();
+            // X is dead until B1 writes its rows [0, 256): bring the encoder weights back into its upper half now, under B1 / B0
+            if (p.use_enc && tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx_s(aux_s, kEncBytes);
+                bulk_g2s(encw, p.encw, kEncBytes, aux_s);
+            }
             dump_rows(dbg_s, 4608, Y, 512, tid);
             {   // B1: g2 (Y,512) -> g1 (X,256)
                 float acc[8][8];
                 acc_zero<8>(acc);
                 gemm_op<8, 2>(acc, Y, kS4, pipe, c);
                 splitk_combine<8>(acc, X, c);
-                if (c.kg == 0) epilogue_bwd<8, 2>(acc, X, kU1, c);
+                if (c.kg == 0) epilogue_bwd<DSOFT, 8, 2>(acc, X, kU1, c);
             }
             gemm_bar();
             dump_rows(dbg_s, 5120, X, 256, tid);
@@ -1101,23 +1143,27 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 float acc[8][2];
                 acc_zero<2>(acc);
                 gemm_op<2>(acc, X, kSB0, pipe, c);
-                epilogue_bwd<2>(acc, Y, -1, c);
+                epilogue_bwd<DSOFT, 2>(acc, Y, -1, c);
             }
             gemm_bar();
             dump_rows(dbg_s, 5376, Y, 128, tid);
 
             // ---- encoder reverse + normalise Jacobian + step: 8 lanes per pose
-            if (p.use_enc) {   // X is free again: park the encoder weights in its upper half, bring the features back
-                for (int i = tid; i < kEncFloats; i += kGemmThreads) encw[i] = __ldg(p.encw + i);
-                const float* stash = p.z0scratch + (size_t)blockIdx.x * 128 * 32;
-                for (int idx = tid; idx < 126 * 32; idx += kGemmThreads) X[swz(idx >> 5, idx & 31)] = stash[idx];
-                gemm_bar();
+            if (p.use_enc) {   // X rows [0, 256) are free again: the encoder weights have landed, bring the features back (one bulk copy)
+                mbar_wait_s(aux_s, aux_phase);
+                aux_phase ^= 1u;
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx_s(aux_s, 128u * 32u * 4u);
+                    bulk_g2s(X, p.z0scratch + (size_t)blockIdx.x * 128 * 32, 128u * 32u * 4u, aux_s);
+                }
+                mbar_wait_s(aux_s, aux_phase);
+                aux_phase ^= 1u;
             }
             {
                 const int m = enc.m;
                 if (p.use_enc) {
-                    if (p.enc_act == ACT_SOFTPLUS) encoder_backward<true>(encw, qs, X, Y, enc, p.enc_beta);
-                    else encoder_backward<false>(encw, qs, X, Y, enc, (p.enc_act == ACT_RELU) ? 0.0f : 0.01f);   // qbar -> Y rows [128, 212)
+                    encoder_backward<ESOFT>(encw, qs, X, Y, enc, ESOFT ? p.enc_beta : ((p.enc_act == ACT_RELU) ? 0.0f : 0.01f));   // qbar -> Y rows [128, 212)
                 } else {
                     for (int e = enc.l; e < 84; e += 8) Y[swz(128 + e, m)] = Y[swz(e, m)];
                     __syncwarp();
@@ -1152,6 +1198,8 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                     }
                 }
             }
+            // the updated tile leaves through the async proxy (bulk store below): make this thread's writes to xs visible to it
+            if (p.pose_out != nullptr) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             gemm_bar();
         }  // steps
 
@@ -1179,19 +1227,17 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                     }
                 }
             }
-            if (p.pose_out != nullptr) {
-                // 16-byte stores (a pose row is 21 float4, a tile starts 16-byte aligned); the same values go to every peer
-                for (int i4 = tid; i4 < nvalid * 21; i4 += kGemmThreads) {
-                    const int m = i4 / 21, e = (i4 - m * 21) * 4;
-                    const float* src = xs + m * kXS + e;
-                    const float4 v = make_float4(src[0], src[1], src[2], src[3]);
-                    reinterpret_cast<float4*>(p.pose_out + pose0 * 84)[i4] = v;
-                    for (int r = 0; r < p.n_peers; ++r) reinterpret_cast<float4*>(p.peer_pose[r] + pose0 * 84)[i4] = v;
-                }
+            if (p.pose_out != nullptr && tid == 0) {
+                // the projected tile is a contiguous image of nvalid x 336 bytes: ONE bulk store, and one more per peer GPU
+                // (fused gather: NVLink-mapped gathered buffers); they drain while the next tile computes
+                bulk_s2g(p.pose_out + pose0 * 84, xs, (uint32_t)nvalid * 336u);
+                for (int r = 0; r < p.n_peers; ++r) bulk_s2g(p.peer_pose[r] + pose0 * 84, xs, (uint32_t)nvalid * 336u);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
         gemm_bar();   // xs / Y are reused by the next tile
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // write-backs complete before the CTA retires
 }
 
 }  // namespace pndf
