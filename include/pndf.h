@@ -223,6 +223,20 @@ int pndf_adam_step(pndf_handle* h, float* param_flat_dev, const float* grad_flat
                    size_t n, double lr, double beta1, double beta2, double eps, double weight_decay, double grad_scale,
                    int64_t step, void* stream);
 
+/* Training-data feed: one trainer batch of PoseData items (model/load_data.py:43-71 __getitem__, :73-77 DataLoader stacking)
+ * assembled in ONE launch from tables resident in device memory: all data files concatenated (pose_table N*84, dist_table N*5
+ * raw neighbour distances, file_off n_files+1 row offsets), all AMASS files concatenated (amass_table, amass_off).  Item i of
+ * the batch uses data file item_file[i] and AMASS file item_amass[i]; every point draws a row of each WITH replacement
+ * (counter-based generator keyed by `seed`, or rows_dev / amass_rows_dev [b*num_pts] to inject the indices), dist = mean of
+ * the 5 stored distances, flip negates quaternions with a negative real part; with flip the reference overwrites the manifold
+ * poses with the flipped noisy poses (load_data.py:63) -- kept unless fix_flip_bug.  Outputs: pose (b*num_pts*84), dist
+ * (b*num_pts), man_poses (b*num_pts*84).  Stateless. */
+int pndf_feed_batch(int device, const float* pose_table_dev, const float* dist_table_dev, const int64_t* file_off_dev,
+                    const float* amass_table_dev, const int64_t* amass_off_dev, const int32_t* item_file_dev,
+                    const int32_t* item_amass_dev, int b, int num_pts, int flip, int fix_flip_bug, uint64_t seed,
+                    const int64_t* rows_dev, const int64_t* amass_rows_dev, float* pose_out_dev, float* dist_out_dev,
+                    float* man_out_dev, void* stream);
+
 /* Rotation formats on either side of the path: pytorch3d.transforms.axis_angle_to_quaternion / quaternion_to_axis_angle
  * (0.7.2; experiments/sample_poses.py:60,80, experiments/motion_denoise.py:81, model/load_data.py:108) on n rotations
  * (n = poses * 21): aa n*3 floats, quat n*4 floats (real part first, 16-byte aligned).  Formulas restated from the

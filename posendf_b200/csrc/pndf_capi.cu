@@ -6,6 +6,7 @@
 #include "pndf_encoder_train.cuh"
 #include "pndf_train_ops.cuh"
 #include "pndf_wgrad.cuh"
+#include "pndf_feed.cuh"
 #include "pndf_knn.cuh"
 
 #include <algorithm>
@@ -907,6 +908,30 @@ int pndf_adam_step(pndf_handle* h, float* param_flat_dev, const float* grad_flat
     h->w_pending = true;
     h->have_weights = true;
     h->launches++;
+    return 0;
+}
+
+int pndf_feed_batch(int device, const float* pose_table_dev, const float* dist_table_dev, const int64_t* file_off_dev,
+                    const float* amass_table_dev, const int64_t* amass_off_dev, const int32_t* item_file_dev,
+                    const int32_t* item_amass_dev, int b, int num_pts, int flip, int fix_flip_bug, uint64_t seed,
+                    const int64_t* rows_dev, const int64_t* amass_rows_dev, float* pose_out_dev, float* dist_out_dev,
+                    float* man_out_dev, void* stream) {
+    if (b == 0 || num_pts == 0) return 0;
+    if (b < 0 || num_pts < 0 || !pose_table_dev || !dist_table_dev || !file_off_dev || !amass_table_dev || !amass_off_dev ||
+        !item_file_dev || !item_amass_dev || !pose_out_dev || !dist_out_dev || !man_out_dev)
+        return fail("pndf_feed_batch: null argument");
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64_t is long long");
+    CUDA_OK(cudaSetDevice(device));
+    FeedParams p{};
+    p.pose_table = pose_table_dev; p.dist_table = dist_table_dev; p.file_off = (const long long*)file_off_dev;
+    p.amass_table = amass_table_dev; p.amass_off = (const long long*)amass_off_dev; p.item_file = item_file_dev;
+    p.item_amass = item_amass_dev; p.rows = (const long long*)rows_dev; p.amass_rows = (const long long*)amass_rows_dev;
+    p.pose_out = pose_out_dev; p.dist_out = dist_out_dev; p.man_out = man_out_dev;
+    p.b = b; p.num_pts = num_pts; p.flip = flip; p.fix_flip_bug = fix_flip_bug; p.seed = seed;
+    const long long warps = (long long)b * num_pts;
+    const unsigned grid = (unsigned)std::min<long long>((warps + 7) / 8, 148LL * 16);
+    feed_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    CUDA_OK(cudaGetLastError());
     return 0;
 }
 

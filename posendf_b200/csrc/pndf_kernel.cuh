@@ -159,9 +159,9 @@ __device__ __forceinline__ float softplus_eval(float v, float beta, float inv_be
 }
 // The same on the SFU (the GEMM epilogues evaluate it 84 000 times per 32-pose tile): e = 2^(bx log2 e) (ex2.approx, 2 ulp),
 // sigma = e / (1 + e) through rcp.approx (1 ulp), log1p(e) = ln2 * lg2(1 + e) (lg2.approx: absolute error < 2^-22 near 1, i.e.
-// < 2e-7 ln2 / beta on the activation).  Validated against the reference's fp64 goldens at the 1e-5 bar for beta = 5, 30,
+// < 2e-7 ln2 / beta on the activation; a short series below e = 2^-6).  Validated against the reference's fp64 goldens at the 1e-5 bar for beta = 5, 30,
 // 100 (tests/test_gpu_parity.py); the exact version above stays in use for the scalar output unit and the encoder.
-__device__ __forceinline__ float softplus_fast(float v, float beta, float inv_beta_ln2, float& deriv) {
+__device__ __forceinline__ float softplus_fast(float v, float beta, float inv_beta, float& deriv) {
     const float bx = v * beta;
     const bool lin = bx > 20.0f;
     float e, r, l;
@@ -170,7 +170,10 @@ __device__ __forceinline__ float softplus_fast(float v, float beta, float inv_be
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(u));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));
     deriv = lin ? 1.0f : e * r;
-    return lin ? v : l * inv_beta_ln2;
+    // small e: lg2(1 + e) would lose e to the rounding of 1 + e (and return 0 below 2^-24, breaking z > 0 and the relation
+    // sigma = 1 - exp(-beta z) the second-order training chain relies on): three series terms, relative error < e^3 / 4
+    const float ln1p = (e < 0.015625f) ? e * fmaf(e, fmaf(e, 0.33333334f, -0.5f), 1.0f) : l * 0.6931471805599453f;
+    return lin ? v : ln1p * inv_beta;
 }
 
 __device__ __forceinline__ float act_eval(float v, int kind, float beta, float& deriv) {
@@ -215,7 +218,7 @@ struct Ctx {
     int tid, lane, mg, ng;
     int ng2, kg;   // split-K ops (N = 256): feature group within a 4-warp K-group, and the K-group (0/1)
     float slope;                       // relu 0 / lrelu 0.01 (piecewise-linear DFNet activation)
-    float df_beta, df_inv_beta_ln2;    // softplus DFNet: beta, ln2 / beta
+    float df_beta, df_inv_beta;        // softplus DFNet: beta, 1 / beta
 };
 
 // KG = number of K-groups an op is split into: KG == 1, all 8 warps tile N = 64*TN features; KG == 2 (split-K, used for
@@ -462,7 +465,7 @@ __device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* o
             const int f = feat_of<TN, KG>(ng, j);
             float z[8], dv[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) z[i] = softplus_fast(acc[i][j], c.df_beta, c.df_inv_beta_ln2, dv[i]);
+            for (int i = 0; i < 8; ++i) z[i] = softplus_fast(acc[i][j], c.df_beta, c.df_inv_beta, dv[i]);
             store_row8(out, f, c.mg, z);
             if (keep_deriv) {
                 float* p = c.dscr + (size_t)(unit_base + f) * 32 + c.mg * 8;
@@ -841,7 +844,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     c.ring_s = smem_u32(c.ring); c.full_s = smem_u32(full + warp * kStages);
     c.tid = tid; c.lane = lane; c.mg = lane >> 3; c.ng = warp * 8 + (lane & 7);
     c.ng2 = (warp & 3) * 8 + (lane & 7); c.kg = warp >> 2;
-    c.slope = (p.df_act == ACT_RELU) ? 0.0f : 0.01f; c.df_beta = p.df_beta; c.df_inv_beta_ln2 = 0.6931471805599453f / p.df_beta;
+    c.slope = (p.df_act == ACT_RELU) ? 0.0f : 0.01f; c.df_beta = p.df_beta; c.df_inv_beta = 1.0f / p.df_beta;
     c.dscr = p.dscratch ? p.dscratch + (size_t)blockIdx.x * kUnits * 32 : nullptr;
     const uint32_t aux_s = smem_u32(full + kWarps * kStages);
     uint32_t aux_phase = 0;

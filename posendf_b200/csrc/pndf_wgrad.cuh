@@ -223,8 +223,7 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(const WgParams p) 
 }
 
 // Last layer (W_6: 1 x 64, b_6) and nothing else: a_6 = phi_out'(s) is recovered from the distance (ReLU: d > 0, softplus:
-// 1 - exp(-beta d)).  One CTA per K-split; thread (kq, n) walks every 4th pose of the split for column n, 4 partials per
-// column are summed in a fixed order.
+// 1 - exp(-beta d)).  One CTA per K-split; 16 pose lanes x 16 column quads, the pose-lane partials are summed in a fixed order.
 struct WgLastParams {
     const float* dump;
     const float* dump_t;
@@ -240,27 +239,42 @@ struct WgLastParams {
 };
 
 __global__ void __launch_bounds__(256) wgrad_last_kernel(const WgLastParams p) {
-    __shared__ float part[4][65];
-    const int n = threadIdx.x & 63, kq = threadIdx.x >> 6;
+    // thread (kq, n4): pose lane kq of 16, columns 4 n4 .. 4 n4 + 3 of z6 -- 16 poses x 256 bytes per iteration, 16-byte loads
+    __shared__ float4 part[16][16];
+    __shared__ float bpart[16];
+    const int n4 = threadIdx.x & 15, kq = threadIdx.x >> 4;
     const long long k0 = (long long)blockIdx.x * kWgKC, kend = min(p.B, k0 + kWgKC);
     const bool has_t = (p.dump_t != nullptr) && (p.w_eik != nullptr);
     const float up = __ldg(p.up), we = has_t ? __ldg(p.w_eik) : 0.0f;
-    float acc = 0.0f, bacc = 0.0f;
-    for (long long k = k0 + kq; k < kend; k += 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float bacc = 0.0f;
+#pragma unroll 4
+    for (long long k = k0 + kq; k < kend; k += 16) {
         const float d = __ldg(p.dist + k);
         const float gs = p.softplus ? -expm1f(-p.beta * d) : (d > 0.0f ? 1.0f : 0.0f);
         const float cb = (p.coef != nullptr) ? up * __ldg(p.coef + k) : up * p.uniform;
-        float r = cb * __ldg(p.dump + k * kDumpRows + p.z6_col + n);
-        if (has_t) r = fmaf(we, __ldg(p.dump_t + k * kDumpRows + p.z6_col + n), r);
-        acc = fmaf(gs, r, acc);
-        if (n == 0) bacc = fmaf(gs, cb, bacc);
+        const float4 z = __ldg(reinterpret_cast<const float4*>(p.dump + k * kDumpRows + p.z6_col) + n4);
+        float4 r = make_float4(cb * z.x, cb * z.y, cb * z.z, cb * z.w);
+        if (has_t) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.dump_t + k * kDumpRows + p.z6_col) + n4);
+            r.x = fmaf(we, t.x, r.x); r.y = fmaf(we, t.y, r.y); r.z = fmaf(we, t.z, r.z); r.w = fmaf(we, t.w, r.w);
+        }
+        acc.x = fmaf(gs, r.x, acc.x); acc.y = fmaf(gs, r.y, acc.y); acc.z = fmaf(gs, r.z, acc.z); acc.w = fmaf(gs, r.w, acc.w);
+        if (n4 == 0) bacc = fmaf(gs, cb, bacc);
     }
-    part[kq][n] = acc;
-    if (n == 0) part[kq][64] = bacc;
+    part[kq][n4] = acc;
+    if (n4 == 0) bpart[kq] = bacc;
     __syncthreads();
     float* ws = p.ws + (size_t)(p.slot0 + blockIdx.x) * (size_t)p.ws_stride;
-    if (threadIdx.x < 64) ws[p.w6_off + threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
-    if (threadIdx.x == 64) ws[p.b6_off] = (part[0][64] + part[1][64]) + (part[2][64] + part[3][64]);
+    if (threadIdx.x < 64) {      // column threadIdx.x: the 16 pose-lane partials in a fixed order
+        float s = 0.0f;
+        for (int q = 0; q < 16; ++q) s += reinterpret_cast<const float*>(&part[q][threadIdx.x >> 2])[threadIdx.x & 3];
+        ws[p.w6_off + threadIdx.x] = s;
+    } else if (threadIdx.x == 64) {
+        float s = 0.0f;
+        for (int q = 0; q < 16; ++q) s += bpart[q];
+        ws[p.b6_off] = s;
+    }
 }
 
 // grad[i] += sum over slots of ws[slot][i] (fixed order) for the DFNet part i >= enc_floats, and the encoder kernel's

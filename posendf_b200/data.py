@@ -5,8 +5,10 @@ The reference opens one `.npz` per item (`{'pose' (N,21,4), 'dist' (N,5), 'nn_po
 data/prepare_traindata.py:173), draws `num_pts` random rows with replacement, averages the 5 kNN distances, and pairs
 them with `num_pts` random rows of ONE randomly chosen AMASS file; the DataLoader stacks `batch_size` such items
 (`shuffle=True, drop_last=True`).  At 262 144 poses per step the per-item `np.load` + fancy indexing on the host is the
-bottleneck, so here every file is loaded ONCE into device memory (fp32; AMASS-scale data is a few GB, HBM has 180) and a
-batch is two `randint` + gather kernels on the device.
+bottleneck, so here every file is read ONCE, concatenated into three tables in HBM (AMASS-scale data is a few GB, HBM has
+180), and a whole batch is ONE launch of the library's feed kernel (pndf_feed_batch, csrc/pndf_feed.cuh: in-kernel
+counter-based row sampling, 336-byte row gather, quaternion flip, mean of the 5 distances).  Host code only plans the epoch
+(file order, which AMASS file per item); there is no CPU / torch implementation of the gather.
 
 Faithful quirks (kept, because a drop-in must feed the trainer the same distribution):
   * rows are sampled WITH replacement (`np.random.randint`), load_data.py:49,60;
@@ -22,14 +24,11 @@ import os
 import numpy as np
 import torch
 
-
-def quat_flip(pose: torch.Tensor) -> torch.Tensor:
-    """negate every quaternion whose real part is negative (load_data.py:12-16)"""
-    return torch.where(pose[..., :1] < 0, -pose, pose)
+from . import _lib
 
 
 class ResidentPoseData:
-    """Iterable of batches `{'pose': (b, n, 21, 4), 'dist': (b, n), 'man_poses': (b, n, 21, 4)}` on `device`."""
+    """Iterable of batches `{'pose': (b, n, 21, 4), 'dist': (b, n), 'man_poses': (b, n, 21, 4)}` on `device` (CUDA)."""
 
     def __init__(self, data_files, amass_files, batch_size=4, num_pts=5000, flip=False, device="cuda", seed=None,
                  fix_flip_bug=False):
@@ -37,17 +36,21 @@ class ResidentPoseData:
             raise ValueError("ResidentPoseData needs at least one data file and one AMASS file")
         self.device = torch.device(device)
         self.batch_size, self.num_pts, self.flip, self.fix_flip_bug = int(batch_size), int(num_pts), bool(flip), bool(fix_flip_bug)
-        self.gen = torch.Generator(device=self.device)
-        self.host_gen = torch.Generator()       # host-side choices (file order, which AMASS file): no device sync per item
-        if seed is not None:
-            self.gen.manual_seed(int(seed))
-            self.host_gen.manual_seed(int(seed))
-        self.pose, self.dist = [], []
+        self.host_gen = np.random.default_rng(seed)       # host-side choices: file order, AMASS file per item, kernel seeds
+        pose, dist, off = [], [], [0]
         for f in data_files:
             z = np.load(f)
-            self.pose.append(torch.from_numpy(np.asarray(z["pose"], dtype=np.float32)).to(self.device))
-            self.dist.append(torch.from_numpy(np.asarray(z["dist"], dtype=np.float32)).mean(dim=1).to(self.device))
-        self.amass = [torch.from_numpy(np.asarray(np.load(f)["pose"], dtype=np.float32)).to(self.device) for f in amass_files]
+            p = np.asarray(z["pose"], dtype=np.float32).reshape(-1, 84)
+            d = np.asarray(z["dist"], dtype=np.float32).reshape(len(p), 5)
+            pose.append(p); dist.append(d); off.append(off[-1] + len(p))
+        am, aoff = [], [0]
+        for f in amass_files:
+            p = np.asarray(np.load(f)["pose"], dtype=np.float32).reshape(-1, 84)
+            am.append(p); aoff.append(aoff[-1] + len(p))
+        self.n_files, self.n_amass = len(data_files), len(amass_files)
+        self.file_off_host, self.amass_off_host = np.asarray(off, dtype=np.int64), np.asarray(aoff, dtype=np.int64)
+        self._host = (np.concatenate(pose), np.concatenate(dist), np.concatenate(am))
+        self._dev = None
 
     @classmethod
     def from_dirs(cls, data_path, amass_dir, splits, **kw):
@@ -57,28 +60,51 @@ class ResidentPoseData:
         return cls(data, amass, **kw)
 
     def __len__(self):
-        return len(self.pose) // self.batch_size          # drop_last=True
+        return self.n_files // self.batch_size          # drop_last=True
 
-    def _randint(self, high, n):
-        return torch.randint(0, high, (n,), device=self.device, generator=self.gen)
+    # ------------------------------------------------------------------ host: epoch plan
+    def plan_epoch(self):
+        """[(item_files (b,), item_amass (b,), kernel seed)] for one epoch: shuffle=True, drop_last=True (load_data.py:75-77);
+        every item gets ONE random AMASS file (load_data.py:57)"""
+        order = self.host_gen.permutation(self.n_files)
+        plan = []
+        for b in range(len(self)):
+            files = order[b * self.batch_size:(b + 1) * self.batch_size].astype(np.int32)
+            amass = self.host_gen.integers(0, self.n_amass, self.batch_size).astype(np.int32)
+            plan.append((files, amass, int(self.host_gen.integers(0, 2 ** 63 - 1))))
+        return plan
 
-    def item(self, idx, rows=None, amass_idx=None, amass_rows=None):
-        """one `PoseData.__getitem__` (indices can be injected for testing)"""
-        rows = self._randint(len(self.pose[idx]), self.num_pts) if rows is None else rows
-        pose = self.pose[idx][rows]
-        if self.flip:
-            pose = quat_flip(pose)
-        dist = self.dist[idx][rows]
-        if amass_idx is None:
-            amass_idx = int(torch.randint(0, len(self.amass), (1,), generator=self.host_gen))
-        amass_rows = self._randint(len(self.amass[amass_idx]), self.num_pts) if amass_rows is None else amass_rows
-        man = self.amass[amass_idx][amass_rows]
-        if self.flip:
-            man = quat_flip(man) if self.fix_flip_bug else pose       # reference bug, see module docstring
+    # ------------------------------------------------------------------ device
+    def _tables(self):
+        if self._dev is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("ResidentPoseData: batches are assembled by the CUDA feed kernel (pndf_feed_batch); there is "
+                                   f"no CPU fallback (device = {self.device})")
+            up = lambda a: torch.from_numpy(a).to(self.device)      # noqa: E731
+            self._dev = tuple(up(a) for a in self._host) + (up(self.file_off_host), up(self.amass_off_host))
+            self._host = None
+        return self._dev
+
+    def batch(self, item_files, item_amass, seed=0, rows=None, amass_rows=None):
+        """one DataLoader batch in ONE launch; rows / amass_rows (b, num_pts) int64 inject the row indices (tests)"""
+        pose_t, dist_t, amass_t, foff, aoff = self._tables()
+        lib = _lib.load()
+        b, n = len(item_files), self.num_pts
+        dev = self.device
+        fi = torch.as_tensor(np.asarray(item_files, dtype=np.int32)).to(dev)
+        ai = torch.as_tensor(np.asarray(item_amass, dtype=np.int32)).to(dev)
+        pose = torch.empty(b, n, 21, 4, device=dev, dtype=torch.float32)
+        dist = torch.empty(b, n, device=dev, dtype=torch.float32)
+        man = torch.empty(b, n, 21, 4, device=dev, dtype=torch.float32)
+        r = None if rows is None else torch.as_tensor(np.asarray(rows, dtype=np.int64)).to(dev).contiguous()
+        ar = None if amass_rows is None else torch.as_tensor(np.asarray(amass_rows, dtype=np.int64)).to(dev).contiguous()
+        _lib.check(lib.pndf_feed_batch(dev.index if dev.index is not None else torch.cuda.current_device(), pose_t.data_ptr(),
+                                       dist_t.data_ptr(), foff.data_ptr(), amass_t.data_ptr(), aoff.data_ptr(), fi.data_ptr(),
+                                       ai.data_ptr(), b, n, int(self.flip), int(self.fix_flip_bug), int(seed) & (2 ** 64 - 1),
+                                       None if r is None else r.data_ptr(), None if ar is None else ar.data_ptr(),
+                                       pose.data_ptr(), dist.data_ptr(), man.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
         return {"pose": pose, "dist": dist, "man_poses": man}
 
     def __iter__(self):
-        order = torch.randperm(len(self.pose), generator=self.host_gen).tolist()                      # shuffle=True
-        for b in range(len(self)):
-            items = [self.item(i) for i in order[b * self.batch_size:(b + 1) * self.batch_size]]
-            yield {k: torch.stack([it[k] for it in items]) for k in ("pose", "dist", "man_poses")}
+        for files, amass, seed in self.plan_epoch():
+            yield self.batch(files, amass, seed)

@@ -1,70 +1,63 @@
-"""CPU: the device-resident data feed reproduces `PoseData.__getitem__` (restated in numpy from
-/root/reference/model/load_data.py:43-71) when given the same indices."""
+"""CPU: host side of the device-resident data feed (posendf_b200/data.py) -- file tables, offsets, the epoch plan (shuffle,
+drop_last, one AMASS file per item) -- and the golden of the REAL reference loader (tests/golden/make_data_golden.py lifts
+PoseData out of /root/reference/model/load_data.py with ast) against an independent numpy restatement.  The gather itself is
+the CUDA feed kernel: tests/test_data_feed.py (-m gpu)."""
+import os
+
 import numpy as np
-import torch
+import pytest
 
-from posendf_b200 import synth
-from posendf_b200.data import ResidentPoseData, quat_flip
+from posendf_b200.data import ResidentPoseData
 
+from golden.make_data_golden import N_AMASS, N_FILES, NUM_PTS, write_files
 
-def _write_files(tmp_path, n_files=5, n_amass=3):
-    data, amass = [], []
-    for i in range(n_files):
-        d = tmp_path / f"ds{i % 2}"
-        d.mkdir(exist_ok=True)
-        n = 200 + 17 * i
-        pose = synth.make_poses(10 + i, n, kind="noisy", sigma=0.3)
-        pose[::3] *= -1                                           # some negative real parts for the flip
-        f = d / f"part{i}_000.npz"
-        np.savez(f, pose=pose, dist=np.abs(synth.normal(20 + i, n * 5)).reshape(n, 5).astype(np.float32), nn_pose=pose[:, None])
-        data.append(str(f))
-    for i in range(n_amass):
-        d = tmp_path / f"am{i}"
-        d.mkdir(exist_ok=True)
-        pose = synth.make_poses(50 + i, 150 + i)
-        pose[1::4] *= -1
-        f = d / f"seq{i}.npz"
-        np.savez(f, pose=pose)
-        amass.append(str(f))
-    return data, amass
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "posedata.npz")
 
 
-def _reference_item(data_file, amass_files, rows, amass_idx, amass_rows, flip):
-    z = np.load(data_file)
-    poses = z["pose"][rows]
-    def qflip(p):
-        q = np.copy(p); neg = p[:, :, 0] < 0; q[np.where(neg)] = -q[np.where(neg)]; return q
-    if flip:
-        poses = qflip(poses)
-    dist = np.mean(z["dist"][rows], axis=1)
-    am = np.load(amass_files[amass_idx])["pose"][amass_rows]
-    if flip:
-        am = qflip(poses)                                          # the reference's own behaviour (load_data.py:63)
-    return poses.astype(np.float32), dist.astype(np.float32), am.astype(np.float32)
-
-
-def test_item_matches_reference_semantics(tmp_path):
-    data, amass = _write_files(tmp_path)
-    rng = np.random.default_rng(0)
-    for flip in (False, True):
-        feed = ResidentPoseData(data, amass, batch_size=2, num_pts=64, flip=flip, device="cpu", seed=1)
-        for idx in range(len(data)):
-            rows = rng.integers(0, len(feed.pose[idx]), 64)
-            ai = int(rng.integers(0, len(amass)))
-            arows = rng.integers(0, len(feed.amass[ai]), 64)
-            it = feed.item(idx, torch.from_numpy(rows), ai, torch.from_numpy(arows))
-            p, d, m = _reference_item(data[idx], amass, rows, ai, arows, flip)
-            assert np.array_equal(it["pose"].numpy(), p) and np.allclose(it["dist"].numpy(), d, rtol=1e-6) and np.array_equal(it["man_poses"].numpy(), m)
-    fixed = ResidentPoseData(data, amass, num_pts=32, flip=True, device="cpu", fix_flip_bug=True).item(0)
-    assert (fixed["man_poses"][..., 0] >= 0).all() and not torch.equal(fixed["man_poses"], fixed["pose"])
-    assert torch.equal(quat_flip(torch.tensor([[-1.0, 2, 3, 4], [1.0, -2, 3, 4]])), torch.tensor([[1.0, -2, -3, -4], [1.0, -2, 3, 4]]))
-
-
-def test_epoch_shapes_shuffle_and_drop_last(tmp_path):
-    data, amass = _write_files(tmp_path)
+def test_tables_offsets_and_epoch_plan(tmp_path):
+    data, amass = write_files(str(tmp_path))
     feed = ResidentPoseData(data, amass, batch_size=2, num_pts=50, device="cpu", seed=3)
-    batches = list(feed)
-    assert len(batches) == len(feed) == 2                          # 5 files, batch 2, drop_last
-    for b in batches:
-        assert b["pose"].shape == (2, 50, 21, 4) and b["dist"].shape == (2, 50) and b["man_poses"].shape == (2, 50, 21, 4)
-        assert b["pose"].dtype == torch.float32 and torch.isfinite(b["dist"]).all()
+    assert feed.n_files == N_FILES and feed.n_amass == N_AMASS
+    pose, dist, am = feed._host
+    for i, f in enumerate(data):
+        z = np.load(f)
+        lo, hi = feed.file_off_host[i], feed.file_off_host[i + 1]
+        assert np.array_equal(pose[lo:hi], z["pose"].reshape(-1, 84)) and np.array_equal(dist[lo:hi], z["dist"])
+    for i, f in enumerate(amass):
+        lo, hi = feed.amass_off_host[i], feed.amass_off_host[i + 1]
+        assert np.array_equal(am[lo:hi], np.load(f)["pose"].reshape(-1, 84))
+    plan = feed.plan_epoch()
+    assert len(plan) == len(feed) == N_FILES // 2                     # drop_last
+    seen = np.concatenate([p[0] for p in plan])
+    assert len(set(seen.tolist())) == len(seen) and set(seen.tolist()) <= set(range(N_FILES))      # a shuffle without repeats
+    for files, am_idx, seed in plan:
+        assert files.dtype == np.int32 and am_idx.dtype == np.int32 and len(files) == len(am_idx) == 2
+        assert (am_idx >= 0).all() and (am_idx < N_AMASS).all() and 0 <= seed < 2 ** 63
+    assert any(not np.array_equal(a[0], b[0]) for a, b in zip(plan, feed.plan_epoch())) or N_FILES < 3      # reshuffled
+
+
+def test_no_cpu_gather():
+    import tempfile
+    with tempfile.TemporaryDirectory() as root:
+        data, amass = write_files(root)
+        feed = ResidentPoseData(data, amass, batch_size=2, num_pts=8, device="cpu")
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            feed.batch([0, 1], [0, 0])
+
+
+def test_reference_golden_matches_numpy_restatement(tmp_path):
+    """pins the meaning of the golden: PoseData.__getitem__ == rows gather, flip, mean of 5, AMASS gather (+ the flip quirk)"""
+    data, amass = write_files(str(tmp_path))
+    z = np.load(GOLD)
+    assert int(z["NUM_PTS"]) == NUM_PTS
+    for flip in (0, 1):
+        for idx in range(N_FILES):
+            t = f"f{flip}_i{idx}"
+            src = np.load(data[idx])
+            rows, ai, arows = z[t + "_rows"], int(z[t + "_amass_idx"]), z[t + "_amass_rows"]
+            pose = src["pose"][rows]
+            if flip:
+                pose = np.where(pose[:, :, :1] < 0, -pose, pose)
+            man = pose if flip else np.load(amass[ai])["pose"][arows]
+            assert np.array_equal(z[t + "_pose"], pose) and np.array_equal(z[t + "_man_poses"], man)
+            assert np.allclose(z[t + "_dist"], src["dist"][rows].mean(axis=1), rtol=1e-6)

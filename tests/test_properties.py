@@ -71,3 +71,37 @@ def test_kernel_matches_oracle_on_random_configs(seed, B, act, beta, kind, wseed
         e = np.linalg.norm((g.cpu().numpy() - gref).reshape(B, -1), axis=1) / np.linalg.norm(gref.reshape(B, -1), axis=1)
         assert np.median(e) < 1e-5
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", ["lrelu", "softplus"])
+def test_kernel_tree_table_perturbing_a_joint_moves_exactly_the_predicted_feature_rows(act):
+    """the KERNEL's copy of the kinematic parent table, read back through the debug dump of the encoder
+    output z0 (rows [0, 126) = joint j's six features at rows 6j .. 6j+5).  Perturbing the quaternion of joint j must change
+    the features of j and of every descendant of j in the reference's table (model/network/net_utils.py:44-50, golden
+    parents.npz) -- and of nothing else.  The perturbation keeps the four column norms of F.normalize(dim=1) fixed (the same
+    joint's quaternion is replaced by another with the same squared components), so only the tree couples joints."""
+    import os
+    from conftest import GOLDEN_DIR
+    from posendf_b200.engine import Engine
+    parents = np.load(os.path.join(GOLDEN_DIR, "parents.npz"))["parents"].tolist()
+    desc = {j: {j} for j in range(21)}
+    for i in range(21):                       # index order is topological
+        p = parents[i]
+        while p >= 0:
+            desc[p].add(i)
+            p = parents[p]
+    eng = Engine(device=0, enc_act=act, df_act=act)
+    eng.set_weights_flat(synth.flatten_params(synth.make_params(1)))
+    x = synth.make_poses(17, 32)
+    base = eng.forward_grad_debug(torch.from_numpy(x).cuda())[2][:, :126].cpu().numpy().reshape(32, 21, 6)
+    for j in range(21):
+        y = x.copy()
+        y[:, j, :] = -y[:, j, :]              # same squares -> same column norms; the joint's normalised input flips sign
+        z0 = eng.forward_grad_debug(torch.from_numpy(y).cuda())[2][:, :126].cpu().numpy().reshape(32, 21, 6)
+        moved = {i for i in range(21) if not np.array_equal(z0[:, i], base[:, i])}
+        assert moved <= desc[j], (j, sorted(moved - desc[j]))
+        # the joint itself always moves; descendants move unless every unit on the path is dead for all 32 poses (relu-like)
+        assert j in moved
+        if act == "softplus":
+            assert moved == desc[j], (j, sorted(desc[j] - moved))

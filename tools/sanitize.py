@@ -27,7 +27,8 @@ for act in ("lrelu", "softplus"):
            "model": {"StrEnc": {"use": True, "act": act, "beta": 100}, "DFNet": {"in_dim": 126, "dims": [256, 512, 1024, 512, 256, 64], "act": act, "beta": 100}}}
     net = PoseNDF(opt)
     net.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_params(2).items()})
-    optim = torch.optim.Adam(net.parameters(), lr=1e-5)
+    from posendf_b200.optim import FusedAdam
+    optim = FusedAdam(net, lr=1e-5, weight_decay=1e-4)
     B = 32 * 3 + 5
     tp = torch.from_numpy(synth.make_poses(5, B, kind="noisy", sigma=0.25)); tm = torch.from_numpy(synth.make_poses(6, B + 9))
     tgt = torch.from_numpy((synth.uniform01(7, B) * 0.5).astype(np.float32))
@@ -46,4 +47,15 @@ cand = torch.randint(0, 500, (37, 50), device="cuda", dtype=torch.int32)
 print("rerank", [t.shape for t in knn_rerank(q, db, cand)])
 from posendf_b200.engine import knn_exact
 print("exact", [t.shape for t in knn_exact(q, db, "geo")], [t.shape for t in knn_exact(q[:3], db[:133], "euc", True)])
+# training-data feed kernel on ragged file sizes
+import tempfile
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from golden.make_data_golden import write_files
+from posendf_b200.data import ResidentPoseData
+with tempfile.TemporaryDirectory() as root:
+    data, amass = write_files(root)
+    for flip in (False, True):
+        feed = ResidentPoseData(data, amass, batch_size=2, num_pts=77, flip=flip, device="cuda", seed=1)
+        print("feed", flip, [tuple(b["pose"].shape) for b in feed])
+torch.cuda.synchronize()
 print("done-train")
