@@ -82,7 +82,8 @@ struct pndf_handle {
     int32_t* d_pos[3] = {nullptr, nullptr, nullptr};   // flat parameter index -> slab-stream position (forward / reverse copy), small-buffer position
     float* d_ws = nullptr;            // split-K workspace [slots][n_params]
     int ws_slots = 0;
-    float* d_encrows = nullptr;       // encoder-gradient accumulators [2][kEncFloats]
+    float* d_encrows = nullptr;       // encoder-gradient rows [2][warps][kEncFloats]
+    long long encrow_warps = 0;
     float* d_loss_partial = nullptr;  // [blocks][2]
     int loss_blocks = 0;
     unsigned int* d_loss_counter = nullptr;
@@ -309,6 +310,17 @@ int ensure_slot(pndf_handle* h, int slot) {
     if (!h->d_z0[slot]) CUDA_OK(cudaMalloc(&h->d_z0[slot], (size_t)h->num_sms * 128 * 32 * sizeof(float)));
     if (h->cfg.df_act == PNDF_ACT_SOFTPLUS && !h->d_scratch[slot])
         CUDA_OK(cudaMalloc(&h->d_scratch[slot], (size_t)h->num_sms * kUnits * 32 * sizeof(float)));
+    return 0;
+}
+
+int ensure_encrows(pndf_handle* h, int64_t B) {
+    const long long nwarps = ((B + 127) / 128) * 4;
+    if (h->encrow_warps < nwarps) {
+        cudaFree(h->d_encrows);
+        h->d_encrows = nullptr;
+        CUDA_OK(cudaMalloc(&h->d_encrows, (size_t)2 * nwarps * kEncFloats * sizeof(float)));
+        h->encrow_warps = nwarps;
+    }
     return 0;
 }
 
@@ -742,14 +754,19 @@ int pndf_encoder_param_grads(pndf_handle* h, const float* pose_dev, const float*
     cudaStream_t st = (cudaStream_t)stream;
     CUDA_OK(cudaMemsetAsync(grads_dev, 0, 2 * kEncFloats * sizeof(float), st));
     if (B == 0) return 0;
+    if (ensure_encrows(h, B)) return 1;
+    const long long nwarps = ((B + 127) / 128) * 4;
     EncTrainParams p{};
     p.x = pose_dev; p.v = v_dev; p.encw = h->d_small + h->off_enc; p.up1 = up_first_dev; p.upt = up_tangent_dev;
-    p.upz = up_second_dev; p.grads = grads_dev; p.B = B; p.normalise = normalise; p.act = h->cfg.enc_act;
+    p.upz = up_second_dev; p.grads = h->d_encrows; p.B = B; p.normalise = normalise; p.act = h->cfg.enc_act;
     p.beta = h->cfg.enc_beta; p.use_enc = 1;
     if (order_after_weights(h, st)) return 1;
     enc_grad_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(p);
     CUDA_OK(cudaGetLastError());
-    h->launches++;
+    const int nsets = (up_tangent_dev || up_second_dev) ? 2 : 1;
+    enc_rows_reduce_kernel<<<(nsets * kEncFloats + 255) / 256, 256, 0, st>>>(h->d_encrows, nwarps, nsets, grads_dev);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 2;
     return 0;
 }
 
@@ -821,7 +838,7 @@ int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_
         CUDA_OK(cudaMalloc(&h->d_ws, (size_t)ksplits * ws_stride * sizeof(float)));
         h->ws_slots = ksplits;
     }
-    if (!h->d_encrows) CUDA_OK(cudaMalloc(&h->d_encrows, 2 * kEncFloats * sizeof(float)));
+    if (h->cfg.use_enc && ensure_encrows(h, B)) return 1;
     static bool attr_set[64] = {};
     if (h->cfg.device < 64 && !attr_set[h->cfg.device]) {
         CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
@@ -863,7 +880,6 @@ int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_
     CUDA_OK(cudaGetLastError());
     int n_enc_rows = 0;
     if (h->cfg.use_enc) {
-        CUDA_OK(cudaMemsetAsync(h->d_encrows, 0, 2 * kEncFloats * sizeof(float), st));
         EncTrainParams ep{};
         ep.x = pose_dev; ep.v = (w_eik_dev || upz_dev) ? v_dev : nullptr; ep.encw = h->d_small + h->off_enc; ep.upz = upz_dev;
         ep.g0 = dump_dev + 5376; ep.g0_ld = kDumpRows; ep.coef = coef_dev; ep.uniform = uniform; ep.up = up_dev;
@@ -871,7 +887,7 @@ int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_
         ep.grads = h->d_encrows; ep.B = B; ep.normalise = normalise; ep.act = h->cfg.enc_act; ep.beta = h->cfg.enc_beta; ep.use_enc = 1;
         enc_grad_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(ep);
         CUDA_OK(cudaGetLastError());
-        n_enc_rows = (ep.weik || ep.upz) ? 2 : 1;
+        n_enc_rows = (int)(((B + 127) / 128) * 4) * ((ep.weik || ep.upz) ? 2 : 1);     // warps x sets, set-major
         h->launches++;
     }
     wgrad_reduce_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, st>>>(h->d_ws, ksplits, (long long)ws_stride, (long long)n_params,

@@ -10,7 +10,8 @@
 //     enc_grad_kernel    : the same forward sweep, then the reverse sweep of BOTH objectives
 //                              O0 = <up1, z0>      O1 = <upt, zdot0> + <upz, z0>
 //                          including the phi'' terms of a softplus encoder, reducing the parameter gradients over the
-//                          warp with shuffles, over the block in shared memory, and over the grid with atomics.
+//                          warp with shuffles into one global row per warp; the rows are summed in a fixed order
+//                          (enc_rows_reduce_kernel / wgrad_reduce_kernel), so the result is deterministic.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -35,7 +36,7 @@ struct EncTrainParams {
     const float* weik;     // device scalar or nullptr (no Eikonal objective)
     int in_dim;            // 126 (row stride of upz)
     float* zdot_tiles;     // [tile][128][32] (tangent kernel)
-    float* grads;          // 2 x 3516 (grad kernel), accumulated with atomics: caller zeroes
+    float* grads;          // grad kernel: per-warp rows [2][warps of the grid][3516] (set 1 rows only if an Eikonal objective is present)
     long long B;
     int normalise, act, use_enc;
     float beta;
@@ -181,7 +182,8 @@ __device__ __forceinline__ float bone_grad_entry(int e, const BoneState& s, cons
     return 0.0f;
 }
 
-// reduce this joint's parameter-gradient terms over the warp and add them to the block accumulator `acc` (shared)
+// reduce this joint's parameter-gradient terms over the warp and store them into this warp's row `acc` (global): every
+// parameter is written exactly once per warp, rows are summed in a fixed order afterwards -> deterministic, no atomics
 template <bool ROOT, int SET>
 __device__ __forceinline__ void bone_grad_reduce(float* acc, const BoneState& s, const BoneAdj& a, int lane) {
     constexpr int n = ROOT ? 116 : 176;
@@ -191,14 +193,14 @@ __device__ __forceinline__ void bone_grad_reduce(float* acc, const BoneState& s,
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = bone_grad_entry<ROOT, SET>(g * 32 + j, s, a);
         const float tot = warp_transpose_sum(v, lane);
-        if (g * 32 + lane < n) atomicAdd(acc + g * 32 + lane, tot);
+        if (g * 32 + lane < n) acc[g * 32 + lane] = tot;
     }
 }
 
 __global__ void __launch_bounds__(128) enc_grad_kernel(const EncTrainParams p) {
-    __shared__ float acc[2 * kEncFloats];
-    for (int i = threadIdx.x; i < 2 * kEncFloats; i += blockDim.x) acc[i] = 0.0f;
-    __syncthreads();
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long wglob = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float* acc = p.grads + wglob * kEncFloats;                         // set 0 row of this warp; set 1 rows follow all set 0 rows
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = b < p.B;
     const long long bb = live ? b : 0;
@@ -286,15 +288,24 @@ __global__ void __launch_bounds__(128) enc_grad_kernel(const EncTrainParams p) {
         // parameter gradients of this joint, reduced over the 32 poses of the warp
         if (root) {
             bone_grad_reduce<true, 0>(acc + off, s, a, lane);
-            if (set1) bone_grad_reduce<true, 1>(acc + kEncFloats + off, s, a, lane);
+            if (set1) bone_grad_reduce<true, 1>(acc + nwarps * kEncFloats + off, s, a, lane);
         } else {
             bone_grad_reduce<false, 0>(acc + off, s, a, lane);
-            if (set1) bone_grad_reduce<false, 1>(acc + kEncFloats + off, s, a, lane);
+            if (set1) bone_grad_reduce<false, 1>(acc + nwarps * kEncFloats + off, s, a, lane);
         }
     }
-    __syncthreads();
-    const int nacc = set1 ? 2 * kEncFloats : kEncFloats;
-    for (int i = threadIdx.x; i < nacc; i += blockDim.x) atomicAdd(p.grads + i, acc[i]);
+}
+
+// out[set][i] = sum over warps of rows[set][warp][i], fixed order
+__global__ void __launch_bounds__(256) enc_rows_reduce_kernel(const float* __restrict__ rows, long long nwarps, int nsets,
+                                                             float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsets * kEncFloats) return;
+    const int set = i / kEncFloats, e = i - set * kEncFloats;
+    const float* r = rows + (size_t)set * nwarps * kEncFloats + e;
+    float s = 0.0f;
+    for (long long w = 0; w < nwarps; ++w) s += r[(size_t)w * kEncFloats];
+    out[i] = s;
 }
 
 }  // namespace pndf

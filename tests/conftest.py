@@ -30,7 +30,7 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_case_names():
-    skip = {"parents", "normalise", "knn_rerank"}
+    skip = {"parents", "normalise", "knn_rerank", "posedata"}
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
                   if os.path.splitext(os.path.basename(p))[0] not in skip)
 
