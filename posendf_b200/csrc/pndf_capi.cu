@@ -21,10 +21,10 @@ using namespace pndf;
 
 namespace pndf {
 using FusedFn = void (*)(const KParams);
-FusedFn pndf_fused_entry_00(int mode);
-FusedFn pndf_fused_entry_01(int mode);
-FusedFn pndf_fused_entry_10(int mode);
-FusedFn pndf_fused_entry_11(int mode);
+FusedFn pndf_fused_entry_00(int mode, int small_tile);
+FusedFn pndf_fused_entry_01(int mode, int small_tile);
+FusedFn pndf_fused_entry_10(int mode, int small_tile);
+FusedFn pndf_fused_entry_11(int mode, int small_tile);
 }  // namespace pndf
 
 namespace {
@@ -42,6 +42,7 @@ int fail(const std::string& msg) {
     } while (0)
 
 const int kAmassDims[6] = {256, 512, 1024, 512, 256, 64};
+const double kSmallTileCost = 0.40;      // time of an 8-pose tile relative to a 32-pose tile (measured)
 
 }  // namespace
 
@@ -301,9 +302,21 @@ __global__ void peer_barrier_kernel(PeerFlags f, int world, int rank, uint32_t e
 
 // the 12 instances of the fused kernel (MODE x softplus DFNet x softplus encoder) live in four translation units
 // (pndf_fused_inst.cu, compiled in parallel)
-FusedFn fused_fn(int mode, bool dsoft, bool esoft) {
-    if (dsoft) return esoft ? pndf_fused_entry_11(mode) : pndf_fused_entry_10(mode);
-    return esoft ? pndf_fused_entry_01(mode) : pndf_fused_entry_00(mode);
+FusedFn fused_fn(int mode, bool dsoft, bool esoft, bool small_tile = false) {
+    if (dsoft) return esoft ? pndf_fused_entry_11(mode, small_tile) : pndf_fused_entry_10(mode, small_tile);
+    return esoft ? pndf_fused_entry_01(mode, small_tile) : pndf_fused_entry_00(mode, small_tile);
+}
+
+// Tile size of a launch.  A 32-pose tile per SM is the latency floor of the main kernel (~0.46 ms forward + reverse), so a batch
+// that cannot give every SM a tile runs the small-tile variant: 8 poses per tile, four times as many CTAs, each ~0.3-0.4 of
+// the time (the four lane groups split K).  It streams the weights once per 8 poses, so it only pays while the 32-pose tiling
+// needs a single round; `PNDF_TILE=8|32` in the environment forces a choice (tests, tuning).
+bool use_small_tile(const pndf_handle* h, const KParams& p, int mode) {
+    if (mode == 2 || p.dbg != nullptr || p.act_masks != nullptr) return false;
+    if (const char* e = getenv("PNDF_TILE")) return atoi(e) == 8;
+    const long long t32 = (p.B + kTileM - 1) / kTileM, t8 = (p.B + 7) / 8;
+    const long long r32 = (t32 + h->num_sms - 1) / h->num_sms, r8 = (t8 + h->num_sms - 1) / h->num_sms;
+    return r32 == 1 && (double)r8 * kSmallTileCost < 0.9;
 }
 
 int ensure_slot(pndf_handle* h, int slot) {
@@ -333,13 +346,14 @@ int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st, int slot = 0) 
     p.encw = h->cfg.use_enc ? h->d_small + h->off_enc : nullptr;
     p.dscratch = h->d_scratch[slot];
     p.z0scratch = h->d_z0[slot];
-    p.ntiles = (int)((p.B + kTileM - 1) / kTileM);
+    const bool small = use_small_tile(h, p, mode);
+    p.ntiles = (int)(small ? (p.B + 7) / 8 : (p.B + kTileM - 1) / kTileM);
     p.use_enc = h->cfg.use_enc; p.enc_act = h->cfg.enc_act; p.df_act = h->cfg.df_act;
     p.enc_beta = h->cfg.enc_beta; p.df_beta = h->cfg.df_beta;
     p.f0_slabs = h->f0_slabs; p.z0_rows = h->z0_rows; p.in_dim = h->cfg.in_dim;
     const int grid = std::min(p.ntiles, h->num_sms);
     if (!h->in_capture && order_after_weights(h, st)) return 1;
-    fused_fn(mode, h->cfg.df_act == PNDF_ACT_SOFTPLUS, h->cfg.enc_act == PNDF_ACT_SOFTPLUS)<<<grid, kThreads, kSmTotal, st>>>(p);
+    fused_fn(mode, h->cfg.df_act == PNDF_ACT_SOFTPLUS, h->cfg.enc_act == PNDF_ACT_SOFTPLUS, small)<<<grid, kThreads, kSmTotal, st>>>(p);
     CUDA_OK(cudaGetLastError());
     h->launches++;
     if (h->in_capture) return 0;       // events must not be recorded into a capture; the caller records after the graph launch
@@ -378,8 +392,9 @@ int pndf_create(const pndf_config* cfg, pndf_handle** out) {
     h->z0_rows = cfg->use_enc ? 128 : 96;
     h->f0_slabs = slabs_of(h->z0_rows, 2, 64);
     for (int mode = 0; mode < 3; ++mode)
-        CUDA_OK(cudaFuncSetAttribute(fused_fn(mode, cfg->df_act == PNDF_ACT_SOFTPLUS, cfg->enc_act == PNDF_ACT_SOFTPLUS),
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
+        for (int small = 0; small < (mode == 2 ? 1 : 2); ++small)
+            CUDA_OK(cudaFuncSetAttribute(fused_fn(mode, cfg->df_act == PNDF_ACT_SOFTPLUS, cfg->enc_act == PNDF_ACT_SOFTPLUS, small != 0),
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmTotal));
     if (ensure_slot(h, 0)) { pndf_destroy(h); return 1; }
     if (cudaEventCreateWithFlags(&h->use_event, cudaEventDisableTiming) != cudaSuccess) { pndf_destroy(h); return fail("cudaEventCreate failed"); }
     if (build_maps(h)) { pndf_destroy(h); return 1; }

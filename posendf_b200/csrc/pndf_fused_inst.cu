@@ -12,8 +12,10 @@
 namespace pndf {
 using FusedFn = void (*)(const KParams);
 // kernel of MODE 0 (forward) / 1 (forward + reverse) / 2 (tangent) for this unit's activation combination
-FusedFn PNDF_ENTRY(PNDF_DSOFT, PNDF_ESOFT)(int mode) {
+// small_tile: the 8-pose-tile variant (MODE 0 / 1 only; the training launches always use 32-pose tiles)
+FusedFn PNDF_ENTRY(PNDF_DSOFT, PNDF_ESOFT)(int mode, int small_tile) {
     constexpr bool D = PNDF_DSOFT != 0, E = PNDF_ESOFT != 0;
+    if (small_tile) return mode == 1 ? pndf_fused_kernel<1, D, E, true> : pndf_fused_kernel<0, D, E, true>;
     if (mode == 1) return pndf_fused_kernel<1, D, E>;
     if (mode == 2) return pndf_fused_kernel<2, D, E>;
     return pndf_fused_kernel<0, D, E>;

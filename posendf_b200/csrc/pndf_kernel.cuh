@@ -217,6 +217,7 @@ struct Ctx {
     float* dscr;   // this CTA's derivative scratch (softplus) or nullptr
     int tid, lane, mg, ng;
     int ng2, kg;   // split-K ops (N = 256): feature group within a 4-warp K-group, and the K-group (0/1)
+    int kq;        // small-tile kernels (KS): this lane group's residue of the reduction rows, lane >> 3 (then mg == 0)
     float slope;                       // relu 0 / lrelu 0.01 (piecewise-linear DFNet activation)
     float df_beta, df_inv_beta;        // softplus DFNet: beta, 1 / beta
 };
@@ -364,10 +365,15 @@ __device__ __forceinline__ void fma_step(float (&acc)[8][TN], const Operands<TN>
 // (R = 1024/(8*TN) reduction rows each; with KG == 2 the warp's K-group covers rows [kg*K/2, (kg+1)*K/2)).
 // The slab body is straight-line code; the next slab's barrier is probed a few rows in, so the ~90-cycle mbarrier
 // round trip hides under the FMAs; the refill of the slab just consumed is issued by the warp itself.
-template <int TN, int KG = 1>
+// KS (small-tile kernels, 8 poses per tile): the four 8-lane groups of a warp no longer own different poses -- all of them
+// multiply the SAME 8 poses (c.mg == 0) and split the reduction rows instead, lane group kq takes rows kq, kq + 4, ... of every
+// slab; kq_reduce() then sums the four partial tiles with two shuffles per accumulator.
+template <int TN, int KG = 1, bool KS = false>
 __device__ __forceinline__ void gemm_op(float (&acc)[8][TN], const float* __restrict__ in, int nslabs, Pipe& pipe,
                                         const Ctx& c) {
     constexpr int R = kSlabFloats / (8 * TN);
+    constexpr int RT = KS ? R / 4 : R;      // rows of a slab this thread multiplies
+    constexpr int RS = KS ? 4 : 1;          // their stride
     const int kbase = (KG == 1) ? 0 : c.kg * (nslabs * R);
     bool ready = mbar_try_wait_s(c.full_s + pipe.stage * 8, pipe.phase);
     for (int s = 0; s < nslabs; ++s) {
@@ -380,17 +386,20 @@ __device__ __forceinline__ void gemm_op(float (&acc)[8][TN], const float* __rest
             // so the thread's two 16-byte pose chunks sit at ((2mg ^ kb) ^ j) and that ^ 1 for row quad j: four offsets per
             // slab, every row is then base + immediate -- no address arithmetic between the FFMA2s.
             const int k0 = kbase + s * R;
-            const float* __restrict__ rows = in + k0 * 32;
+            const float* __restrict__ rows = in + (k0 + (KS ? c.kq : 0)) * 32;
+            const float* __restrict__ wk = w + (KS ? c.kq * 64 : 0);
             const int cb = (c.mg * 2) ^ ((k0 >> 2) & 4);
             const int ngl4 = (c.lane & 7) * 4;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (r == 4) ready = mbar_try_wait_s(c.full_s + pipe.stage * 8, pipe.phase);
+            for (int rr = 0; rr < RT; ++rr) {
+                constexpr int kProbe = KS ? 1 : 4;
+                if (rr == kProbe) ready = mbar_try_wait_s(c.full_s + pipe.stage * 8, pipe.phase);
+                const int r = rr * RS;      // (+ kq, folded into the base pointers: the swizzle key only depends on r >> 2)
                 const int ca = (cb ^ (r >> 2)) << 2;
                 const float4 a0 = *reinterpret_cast<const float4*>(rows + r * 32 + ca);
                 const float4 a1 = *reinterpret_cast<const float4*>(rows + r * 32 + (ca ^ 4));
-                const float4 b0 = *reinterpret_cast<const float4*>(w + r * 64 + ngl4);
-                const float4 b1 = *reinterpret_cast<const float4*>(w + r * 64 + 32 + ngl4);
+                const float4 b0 = *reinterpret_cast<const float4*>(wk + r * 64 + ngl4);
+                const float4 b1 = *reinterpret_cast<const float4*>(wk + r * 64 + 32 + ngl4);
                 Operands<TN> o;
                 o.a[0] = a0.x; o.a[1] = a0.y; o.a[2] = a0.z; o.a[3] = a0.w;
                 o.a[4] = a1.x; o.a[5] = a1.y; o.a[6] = a1.z; o.a[7] = a1.w;
@@ -399,9 +408,10 @@ __device__ __forceinline__ void gemm_op(float (&acc)[8][TN], const float* __rest
                 fma_step<TN>(acc, o);
             }
         } else {
-#pragma unroll (R > 32 ? 32 : R)
-            for (int r = 0; r < R; ++r) {
-                if (r == 4) ready = mbar_try_wait_s(c.full_s + pipe.stage * 8, pipe.phase);
+#pragma unroll (RT > 32 ? 32 : RT)
+            for (int rr = 0; rr < RT; ++rr) {
+                if (rr == 4) ready = mbar_try_wait_s(c.full_s + pipe.stage * 8, pipe.phase);
+                const int r = rr * RS + (KS ? c.kq : 0);
                 Operands<TN> o;
                 load_operands<TN>(o, in, kbase + s * R + r, w, r, c);
                 fma_step<TN>(acc, o);
@@ -410,6 +420,30 @@ __device__ __forceinline__ void gemm_op(float (&acc)[8][TN], const float* __rest
         __syncwarp();
         refill(pipe, c, cur);
     }
+}
+
+// KS: sum the four lane groups' partial tiles (every lane ends up with the full sums of its 8 poses x TN features)
+template <int TN, bool KS>
+__device__ __forceinline__ void kq_reduce(float (&acc)[8][TN]) {
+    if (!KS) return;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            float v = acc[i][j];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            acc[i][j] = v;
+        }
+}
+// KS: after kq_reduce the four lane groups hold identical tiles; feature j of the thread's TN is finished (epilogue, stores)
+// by exactly one of them
+template <int TN, bool KS>
+__device__ __forceinline__ bool owns(int j, int kq) {
+    if (!KS) return true;
+    if (TN == 8) return (j >> 1) == kq;
+    if (TN == 2) return j == kq;
+    return kq == 0;
 }
 
 // write one feature row segment (8 poses of this thread) into a [feature][pose] buffer
@@ -455,13 +489,14 @@ __device__ __forceinline__ void mask_load(const uint8_t* mask, int mg, int unit0
 
 // forward epilogue: z = act(acc) (bias already in acc), remember the derivative, store z as next input.
 // unit_base: index of feature 0 of this op in the mask / scratch unit space.
-template <bool SOFT, int TN, int KG = 1>
+template <bool SOFT, int TN, int KG = 1, bool KS = false>
 __device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* out, int unit_base, const Ctx& c, bool keep_deriv) {
     const int ng = ngv<KG>(c);
     const int unit0 = unit_base + feat_of<TN, KG>(ng, 0);
     if (SOFT) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
+            if (!owns<TN, KS>(j, c.kq)) continue;
             const int f = feat_of<TN, KG>(ng, j);
             float z[8], dv[8];
 #pragma unroll
@@ -478,6 +513,7 @@ __device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* o
         uint32_t bits[TN];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
+            if (!owns<TN, KS>(j, c.kq)) continue;
             const int f = feat_of<TN, KG>(ng, j);
             float z[8];
             uint32_t bm = 0;
@@ -490,19 +526,21 @@ __device__ __forceinline__ void epilogue_fwd(const float (&acc)[8][TN], float* o
             }
             bits[j] = bm;
             store_row8(out, f, c.mg, z);
+            if (KS && keep_deriv) c.mask[unit_base + f] = (uint8_t)bm;      // plane 0, one byte per unit
         }
-        if (keep_deriv) mask_store<TN, KG>(c.mask, c.mg, unit0, bits);
+        if (!KS && keep_deriv) mask_store<TN, KG>(c.mask, c.mg, unit0, bits);
     }
 }
 
 // reverse epilogue: g = acc * act'(pre) of the layer whose input-gradient this op produced; store as the
 // next reverse op's input.  unit_base < 0: no derivative (the encoder features, handled by the encoder).
-template <bool SOFT, int TN, int KG = 1>
+template <bool SOFT, int TN, int KG = 1, bool KS = false>
 __device__ __forceinline__ void epilogue_bwd(const float (&acc)[8][TN], float* out, int unit_base, const Ctx& c) {
     const int ng = ngv<KG>(c);
     if (unit_base < 0) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
+            if (!owns<TN, KS>(j, c.kq)) continue;
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = acc[i][j];
@@ -513,6 +551,7 @@ __device__ __forceinline__ void epilogue_bwd(const float (&acc)[8][TN], float* o
     if (SOFT) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
+            if (!owns<TN, KS>(j, c.kq)) continue;
             const int f = feat_of<TN, KG>(ng, j);
             const float* p = c.dscr + (size_t)(unit_base + f) * 32 + c.mg * 8;
             const float4 d0 = *reinterpret_cast<const float4*>(p);
@@ -526,9 +565,11 @@ __device__ __forceinline__ void epilogue_bwd(const float (&acc)[8][TN], float* o
     } else {
         const float slope = c.slope;
         uint32_t bits[TN];
-        mask_load<TN, KG>(c.mask, c.mg, unit_base + feat_of<TN, KG>(ng, 0), bits);
+        if (!KS) mask_load<TN, KG>(c.mask, c.mg, unit_base + feat_of<TN, KG>(ng, 0), bits);
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
+            if (!owns<TN, KS>(j, c.kq)) continue;
+            if (KS) bits[j] = c.mask[unit_base + feat_of<TN, KG>(ng, j)];
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = ((bits[j] >> i) & 1u) ? acc[i][j] : acc[i][j] * slope;
@@ -539,11 +580,12 @@ __device__ __forceinline__ void epilogue_bwd(const float (&acc)[8][TN], float* o
 
 // split-K ops: K-group 1 parks its partial sums in the op's output tile, K-group 0 adds them to its own and then
 // runs the epilogue over the same elements (same thread <-> element mapping in both groups).
-template <int TN>
+template <int TN, bool KS = false>
 __device__ __forceinline__ void splitk_combine(float (&acc)[8][TN], float* out, const Ctx& c) {
     if (c.kg == 1) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
+            if (!owns<TN, KS>(j, c.kq)) continue;
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = acc[i][j];
@@ -554,6 +596,7 @@ __device__ __forceinline__ void splitk_combine(float (&acc)[8][TN], float* out, 
     if (c.kg == 0) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
+            if (!owns<TN, KS>(j, c.kq)) continue;
             const int f = feat_of<TN, 2>(c.ng2, j);
             const int key = (f >> 2) & 7;
             const float* row = out + f * 32;
@@ -799,8 +842,13 @@ __device__ __forceinline__ void aa_to_quat_vjp(const float (&a)[3], const float 
 // the second launch of a training step (Eikonal term), see posendf_b200/train.py.
 // DSOFT / ESOFT: softplus DFNet / encoder (else piecewise-linear, slope from the config) -- compile-time, so every activation
 // combination is its own kernel without the other variant's code in its epilogues.
-template <int MODE, bool DSOFT, bool ESOFT>
+// KS: small-tile variant (8 poses per tile, the lane groups split the reduction rows; see gemm_op) for batches that cannot
+// fill the SMs with 32-pose tiles -- the reference's real call sites run B = 10 (experiments/sample_poses.py:96) and one motion
+// sequence (experiments/motion_denoise.py:133-137).  Same buffers and layouts, only pose columns [0, 8) of a tile are live.
+template <int MODE, bool DSOFT, bool ESOFT, bool KS = false>
 __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p) {
+    static_assert(!(KS && MODE == 2), "the training launches always use 32-pose tiles");
+    constexpr int kTilePoses = KS ? 8 : kTileM;
     constexpr bool kGrad = (MODE == 1);
     extern __shared__ __align__(1024) uint8_t smem[];
     float* X = reinterpret_cast<float*>(smem + kSmX);
@@ -842,7 +890,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     Ctx c;
     c.X = X; c.Y = Y; c.ring = ring + warp * (kStages * kSlabFloats); c.mask = mask;
     c.ring_s = smem_u32(c.ring); c.full_s = smem_u32(full + warp * kStages);
-    c.tid = tid; c.lane = lane; c.mg = lane >> 3; c.ng = warp * 8 + (lane & 7);
+    c.tid = tid; c.lane = lane; c.mg = KS ? 0 : (lane >> 3); c.kq = lane >> 3; c.ng = warp * 8 + (lane & 7);
     c.ng2 = (warp & 3) * 8 + (lane & 7); c.kg = warp >> 2;
     c.slope = (p.df_act == ACT_RELU) ? 0.0f : 0.01f; c.df_beta = p.df_beta; c.df_inv_beta = 1.0f / p.df_beta;
     c.dscr = p.dscratch ? p.dscratch + (size_t)blockIdx.x * kUnits * 32 : nullptr;
@@ -866,8 +914,8 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     }
 
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-        const long long pose0 = (long long)tile * kTileM;
-        const int nvalid = (int)min((long long)kTileM, p.B - pose0);
+        const long long pose0 = (long long)tile * kTilePoses;
+        const int nvalid = (int)min((long long)kTilePoses, p.B - pose0);
         float* dbg = (p.dbg == nullptr) ? nullptr
                      : (p.dump_all ? p.dbg + (size_t)tile * kDumpRows * 32 : (tile == 0 ? p.dbg : nullptr));
 
@@ -988,17 +1036,17 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             {   // F0: z0 (X) -> z1 (Y), 256 wide
                 float acc[8][8];
                 if (c.kg == 0 && !tangent) acc_init_bias<8, 2>(acc, p.bias[0], c.ng2, 256); else acc_zero<8>(acc);
-                gemm_op<8, 2>(acc, X, p.f0_slabs, pipe, c);
-                splitk_combine<8>(acc, Y, c);
-                if (c.kg == 0) { if (!tangent) epilogue_fwd<DSOFT, 8, 2>(acc, Y, kU1, c, keep); else epilogue_bwd<DSOFT, 8, 2>(acc, Y, kU1, c); }
+                gemm_op<8, 2, KS>(acc, X, p.f0_slabs, pipe, c); kq_reduce<8, KS>(acc);
+                splitk_combine<8, KS>(acc, Y, c);
+                if (c.kg == 0) { if (!tangent) epilogue_fwd<DSOFT, 8, 2, KS>(acc, Y, kU1, c, keep); else epilogue_bwd<DSOFT, 8, 2, KS>(acc, Y, kU1, c); }
             }
             gemm_bar();
             dump_rows(dbg_p, 128, Y, 256, tid);
             {   // F1: z1 (Y) -> z2 (X), 512 wide
                 float acc[8][8];
                 if (!tangent) acc_init_bias<8>(acc, p.bias[1], c.ng, 512); else acc_zero<8>(acc);
-                gemm_op<8>(acc, Y, kS1, pipe, c);
-                if (!tangent) epilogue_fwd<DSOFT, 8>(acc, X, kU2, c, keep); else epilogue_bwd<DSOFT, 8>(acc, X, kU2, c);
+                gemm_op<8, 1, KS>(acc, Y, kS1, pipe, c); kq_reduce<8, KS>(acc);
+                if (!tangent) epilogue_fwd<DSOFT, 8, 1, KS>(acc, X, kU2, c, keep); else epilogue_bwd<DSOFT, 8, 1, KS>(acc, X, kU2, c);
             }
             gemm_bar();
             dump_rows(dbg_p, 384, X, 512, tid);
@@ -1008,31 +1056,32 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 for (int ch = 0; ch < 2; ++ch) {
                     float acc2[8][8];
                     if (!tangent) acc_init_bias<8>(acc2, p.bias[2] + ch * 512, c.ng, 512); else acc_zero<8>(acc2);
-                    gemm_op<8>(acc2, X, kS23, pipe, c);
-                    if (!tangent) epilogue_fwd<DSOFT, 8>(acc2, Y, kU3 + ch * 512, c, keep); else epilogue_bwd<DSOFT, 8>(acc2, Y, kU3 + ch * 512, c);
+                    gemm_op<8, 1, KS>(acc2, X, kS23, pipe, c); kq_reduce<8, KS>(acc2);
+                    if (!tangent) epilogue_fwd<DSOFT, 8, 1, KS>(acc2, Y, kU3 + ch * 512, c, keep); else epilogue_bwd<DSOFT, 8, 1, KS>(acc2, Y, kU3 + ch * 512, c);
                     gemm_bar();
                     dump_rows(dbg_p, 896 + ch * 512, Y, 512, tid);
-                    gemm_op<8>(acc3, Y, kS23, pipe, c);
+                    gemm_op<8, 1, KS>(acc3, Y, kS23, pipe, c);
                     gemm_bar();
                 }
-                if (!tangent) epilogue_fwd<DSOFT, 8>(acc3, X, kU4, c, keep); else epilogue_bwd<DSOFT, 8>(acc3, X, kU4, c);
+                kq_reduce<8, KS>(acc3);
+                if (!tangent) epilogue_fwd<DSOFT, 8, 1, KS>(acc3, X, kU4, c, keep); else epilogue_bwd<DSOFT, 8, 1, KS>(acc3, X, kU4, c);
             }
             gemm_bar();
             dump_rows(dbg_p, 1920, X, 512, tid);
             {   // F4: z4 (X) -> z5 (Y), 256 wide
                 float acc[8][8];
                 if (c.kg == 0 && !tangent) acc_init_bias<8, 2>(acc, p.bias[4], c.ng2, 256); else acc_zero<8>(acc);
-                gemm_op<8, 2>(acc, X, kS4, pipe, c);
-                splitk_combine<8>(acc, Y, c);
-                if (c.kg == 0) { if (!tangent) epilogue_fwd<DSOFT, 8, 2>(acc, Y, kU5, c, keep); else epilogue_bwd<DSOFT, 8, 2>(acc, Y, kU5, c); }
+                gemm_op<8, 2, KS>(acc, X, kS4, pipe, c); kq_reduce<8, KS>(acc);
+                splitk_combine<8, KS>(acc, Y, c);
+                if (c.kg == 0) { if (!tangent) epilogue_fwd<DSOFT, 8, 2, KS>(acc, Y, kU5, c, keep); else epilogue_bwd<DSOFT, 8, 2, KS>(acc, Y, kU5, c); }
             }
             gemm_bar();
             dump_rows(dbg_p, 2432, Y, 256, tid);
             {   // F5: z5 (Y) -> z6 (X), 64 wide
                 float acc[8][1];
                 if (!tangent) acc_init_bias<1>(acc, p.bias[5], c.ng, 64); else acc_zero<1>(acc);
-                gemm_op<1>(acc, Y, kS5, pipe, c);
-                if (!tangent) epilogue_fwd<DSOFT, 1>(acc, X, kU6, c, keep); else epilogue_bwd<DSOFT, 1>(acc, X, kU6, c);
+                gemm_op<1, 1, KS>(acc, Y, kS5, pipe, c); kq_reduce<1, KS>(acc);
+                if (!tangent) epilogue_fwd<DSOFT, 1, 1, KS>(acc, X, kU6, c, keep); else epilogue_bwd<DSOFT, 1, 1, KS>(acc, X, kU6, c);
             }
             gemm_bar();
             dump_rows(dbg_p, 2688, X, 64, tid);
@@ -1096,17 +1145,17 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             {   // B5: g6 (Y,64) -> g5 (X,256)
                 float acc[8][8];
                 acc_zero<8>(acc);
-                gemm_op<8, 2>(acc, Y, kSB5, pipe, c);
-                splitk_combine<8>(acc, X, c);
-                if (c.kg == 0) epilogue_bwd<DSOFT, 8, 2>(acc, X, kU5, c);
+                gemm_op<8, 2, KS>(acc, Y, kSB5, pipe, c); kq_reduce<8, KS>(acc);
+                splitk_combine<8, KS>(acc, X, c);
+                if (c.kg == 0) epilogue_bwd<DSOFT, 8, 2, KS>(acc, X, kU5, c);
             }
             gemm_bar();
             dump_rows(dbg_s, 2816, X, 256, tid);
             {   // B4: g5 (X,256) -> g4 (Y,512)
                 float acc[8][8];
                 acc_zero<8>(acc);
-                gemm_op<8>(acc, X, kS1, pipe, c);
-                epilogue_bwd<DSOFT, 8>(acc, Y, kU4, c);
+                gemm_op<8, 1, KS>(acc, X, kS1, pipe, c); kq_reduce<8, KS>(acc);
+                epilogue_bwd<DSOFT, 8, 1, KS>(acc, Y, kU4, c);
             }
             gemm_bar();
             dump_rows(dbg_s, 3072, Y, 512, tid);
@@ -1116,14 +1165,15 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
                 for (int ch = 0; ch < 2; ++ch) {
                     float accb3[8][8];
                     acc_zero<8>(accb3);
-                    gemm_op<8>(accb3, Y, kS23, pipe, c);
-                    epilogue_bwd<DSOFT, 8>(accb3, X, kU3 + ch * 512, c);
+                    gemm_op<8, 1, KS>(accb3, Y, kS23, pipe, c); kq_reduce<8, KS>(accb3);
+                    epilogue_bwd<DSOFT, 8, 1, KS>(accb3, X, kU3 + ch * 512, c);
                     gemm_bar();
                     dump_rows(dbg_s, 3584 + ch * 512, X, 512, tid);
-                    gemm_op<8>(accb2, X, kS23, pipe, c);
+                    gemm_op<8, 1, KS>(accb2, X, kS23, pipe, c);
                     gemm_bar();
                 }
-                epilogue_bwd<DSOFT, 8>(accb2, Y, kU2, c);
+                kq_reduce<8, KS>(accb2);
+                epilogue_bwd<DSOFT, 8, 1, KS>(accb2, Y, kU2, c);
             }
             gemm_bar();
             // X is dead until B1 writes its rows [0, 256): bring the encoder weights back into its upper half now, under B1 / B0
@@ -1136,17 +1186,17 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             {   // B1: g2 (Y,512) -> g1 (X,256)
                 float acc[8][8];
                 acc_zero<8>(acc);
-                gemm_op<8, 2>(acc, Y, kS4, pipe, c);
-                splitk_combine<8>(acc, X, c);
-                if (c.kg == 0) epilogue_bwd<DSOFT, 8, 2>(acc, X, kU1, c);
+                gemm_op<8, 2, KS>(acc, Y, kS4, pipe, c); kq_reduce<8, KS>(acc);
+                splitk_combine<8, KS>(acc, X, c);
+                if (c.kg == 0) epilogue_bwd<DSOFT, 8, 2, KS>(acc, X, kU1, c);
             }
             gemm_bar();
             dump_rows(dbg_s, 5120, X, 256, tid);
             {   // B0: g1 (X,256) -> g0 (Y,128)
                 float acc[8][2];
                 acc_zero<2>(acc);
-                gemm_op<2>(acc, X, kSB0, pipe, c);
-                epilogue_bwd<DSOFT, 2>(acc, Y, -1, c);
+                gemm_op<2, 1, KS>(acc, X, kSB0, pipe, c); kq_reduce<2, KS>(acc);
+                epilogue_bwd<DSOFT, 2, 1, KS>(acc, Y, -1, c);
             }
             gemm_bar();
             dump_rows(dbg_s, 5376, Y, 128, tid);

@@ -13,6 +13,17 @@ from posendf_b200 import synth
 
 pytestmark = pytest.mark.gpu
 CASES = golden_case_names()
+
+
+@pytest.fixture(autouse=True, params=["auto", "32", "8"])
+def tile_size(request, monkeypatch):
+    """every test of this file runs with the library's own choice of tile (32-pose tiles, or the 8-pose small-tile kernels for
+    batches that cannot fill the SMs) and with either kernel family forced (PNDF_TILE, csrc/pndf_capi.cu::use_small_tile)"""
+    if request.param == "auto":
+        monkeypatch.delenv("PNDF_TILE", raising=False)
+    else:
+        monkeypatch.setenv("PNDF_TILE", request.param)
+    return request.param
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 
 

@@ -234,14 +234,15 @@ def test_gradient_accumulation_semantics_of_the_flat_buffer():
     g1 = net.flat_grad().clone()
     assert net.grads_attached() and g1.abs().sum().item() > 0
     run()                                                     # attached -> accumulates
-    assert torch.allclose(net.flat_grad(), 2 * g1, rtol=1e-6, atol=0)
+    # (g1 + pose part) + manifold part vs 2 (pose part + manifold part): equal up to fp32 rounding of the running sum
+    assert torch.allclose(net.flat_grad(), 2 * g1, rtol=1e-5, atol=1e-6 * g1.abs().max().item())
     net.zero_grad()                                           # torch default: grads -> None
     run()
     assert torch.equal(net.flat_grad(), g1)                   # overwritten, deterministic
     for p in net.parameters():                                # foreign gradient tensors are carried over
         p.grad = torch.ones_like(p)
     run()
-    assert torch.allclose(net.flat_grad(), g1 + 1.0, rtol=1e-6, atol=1e-7) and net.grads_attached()
+    assert torch.allclose(net.flat_grad(), g1 + 1.0, rtol=1e-5, atol=1e-6) and net.grads_attached()
 
 
 def test_fused_adam_matches_torch_adam_and_keeps_the_packed_weights_current():
