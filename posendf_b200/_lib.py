@@ -61,6 +61,8 @@ SYMBOLS = {
     "pndf_quaternion_to_axis_angle": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pndf_knn_rerank": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pndf_knn_exact": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pndf_set_tile_policy": (C.c_int, [C.c_void_p, C.c_int]),
+    "pndf_tile_for_batch": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int)]),
     "pndf_fp32_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "pndf_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "pndf_num_sms": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),

@@ -95,6 +95,7 @@ struct pndf_handle {
     cudaStream_t cap_stream = nullptr;   // graph capture of the denoise loop
     cudaGraphExec_t dn_exec = nullptr;
     bool in_capture = false;
+    int tile_policy = 0;                 // 0: per launch from its batch size (use_small_tile), 8 / 32: pinned (pndf_set_tile_policy)
 };
 
 namespace {
@@ -311,12 +312,16 @@ FusedFn fused_fn(int mode, bool dsoft, bool esoft, bool small_tile = false) {
 // that cannot give every SM a tile runs the small-tile variant: 8 poses per tile, four times as many CTAs, each ~0.3-0.4 of
 // the time (the four lane groups split K).  It streams the weights once per 8 poses, so it only pays while the 32-pose tiling
 // needs a single round; `PNDF_TILE=8|32` in the environment forces a choice (tests, tuning).
+bool small_tile_for(const pndf_handle* h, long long B) {
+    const long long t32 = (B + kTileM - 1) / kTileM, t8 = (B + 7) / 8;
+    const long long r32 = (t32 + h->num_sms - 1) / h->num_sms, r8 = (t8 + h->num_sms - 1) / h->num_sms;
+    return r32 == 1 && (double)r8 * kSmallTileCost < 0.9;
+}
 bool use_small_tile(const pndf_handle* h, const KParams& p, int mode) {
     if (mode == 2 || p.dbg != nullptr || p.act_masks != nullptr) return false;
     if (const char* e = getenv("PNDF_TILE")) return atoi(e) == 8;
-    const long long t32 = (p.B + kTileM - 1) / kTileM, t8 = (p.B + 7) / 8;
-    const long long r32 = (t32 + h->num_sms - 1) / h->num_sms, r8 = (t8 + h->num_sms - 1) / h->num_sms;
-    return r32 == 1 && (double)r8 * kSmallTileCost < 0.9;
+    if (h->tile_policy != 0) return h->tile_policy == 8;
+    return small_tile_for(h, p.B);
 }
 
 int ensure_slot(pndf_handle* h, int slot) {
@@ -331,7 +336,8 @@ int ensure_encrows(pndf_handle* h, int64_t B) {
     if (h->encrow_warps < nwarps) {
         cudaFree(h->d_encrows);
         h->d_encrows = nullptr;
-        CUDA_OK(cudaMalloc(&h->d_encrows, (size_t)2 * nwarps * kEncFloats * sizeof(float)));
+        // per-warp rows [2][nwarps][E] followed by the first-level partial sums [2][kEncChunks][E]
+        CUDA_OK(cudaMalloc(&h->d_encrows, ((size_t)2 * nwarps + 2 * kEncChunks) * kEncFloats * sizeof(float)));
         h->encrow_warps = nwarps;
     }
     return 0;
@@ -587,6 +593,10 @@ int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out
         h->chunk_poses = chunk;
     }
     if (ensure_slot(h, 1) || ensure_slot(h, 2)) return 1;   // the two streams overlap: each needs its own per-CTA scratch
+    // one tile size for all chunks, the one the whole batch would get: the result equals pndf_project on the same batch bit for bit
+    const int saved_policy = h->tile_policy;
+    if (saved_policy == 0) h->tile_policy = small_tile_for(h, B) ? 8 : 32;
+    struct Restore { pndf_handle* h; int v; ~Restore() { h->tile_policy = v; } } restore{h, saved_policy};
     int which = 0;
     for (int64_t off = 0; off < B; off += chunk, which ^= 1) {
         const int64_t nb = std::min(chunk, B - off);
@@ -846,7 +856,21 @@ int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n_params = param_count(&h->cfg);
     const size_t ws_stride = (n_params + 3) & ~(size_t)3;      // 16-byte aligned workspace slots (vector stores)
-    const int ksplits = (int)((B + kWgKC - 1) / kWgKC);
+    // K-split length: 84 output tiles per split, 2 CTAs per SM -- pick the multiple of 32 poses in [768, 1536] that wastes the
+    // least of the last wave (B = 32 768: 864 poses -> 38 splits, 3 192 CTAs = 10.8 waves of 296)
+    const int kTiles = 84;
+    int kc = 1024;
+    {
+        const long long slots = 2LL * h->num_sms;
+        long long best = -1;
+        for (int cand = 768; cand <= 1536; cand += kWgBK) {
+            const long long splits = (B + cand - 1) / cand;
+            const long long waves = (kTiles * splits + slots - 1) / slots;
+            const long long cost = waves * cand;
+            if (best < 0 || cost < best) { best = cost; kc = cand; }
+        }
+    }
+    const int ksplits = (int)((B + kc - 1) / kc);
     if (h->ws_slots < ksplits) {
         cudaFree(h->d_ws);
         h->d_ws = nullptr;
@@ -872,7 +896,7 @@ int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_
     const int a_col[6] = {5120, 4608, 3584, 3072, 2816, 2752};
     WgParams p{};
     p.dump = dump_dev; p.dump_t = dump_t_dev; p.coef = coef_dev; p.up = up_dev; p.w_eik = w_eik_dev; p.uniform = uniform;
-    p.ws = h->d_ws; p.B = B; p.ws_stride = (long long)ws_stride; p.slot0 = 0; p.nprob = 6;
+    p.ws = h->d_ws; p.B = B; p.ws_stride = (long long)ws_stride; p.kc = kc; p.slot0 = 0; p.nprob = 6;
     int tiles = 0;
     // big layers first: their CTAs start first inside every K-split
     const int order[6] = {2, 3, 1, 4, 0, 5};
@@ -890,10 +914,11 @@ int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_
     WgLastParams lp{};
     lp.dump = dump_dev; lp.dump_t = dump_t_dev; lp.coef = coef_dev; lp.up = up_dev; lp.w_eik = w_eik_dev; lp.dist = dist_dev;
     lp.uniform = uniform; lp.ws = h->d_ws; lp.B = B; lp.ws_stride = (long long)ws_stride; lp.w6_off = w_off[6]; lp.b6_off = b_off[6];
-    lp.slot0 = 0; lp.z6_col = z_col[6]; lp.softplus = (h->cfg.df_act == PNDF_ACT_SOFTPLUS); lp.beta = h->cfg.df_beta;
+    lp.kc = kc; lp.slot0 = 0; lp.z6_col = z_col[6]; lp.softplus = (h->cfg.df_act == PNDF_ACT_SOFTPLUS); lp.beta = h->cfg.df_beta;
     wgrad_last_kernel<<<(unsigned)ksplits, 256, 0, st>>>(lp);
     CUDA_OK(cudaGetLastError());
     int n_enc_rows = 0;
+    float* enc_part = nullptr;
     if (h->cfg.use_enc) {
         EncTrainParams ep{};
         ep.x = pose_dev; ep.v = (w_eik_dev || upz_dev) ? v_dev : nullptr; ep.encw = h->d_small + h->off_enc; ep.upz = upz_dev;
@@ -902,11 +927,16 @@ int pndf_wgrad_accumulate(pndf_handle* h, const float* pose_dev, const float* v_
         ep.grads = h->d_encrows; ep.B = B; ep.normalise = normalise; ep.act = h->cfg.enc_act; ep.beta = h->cfg.enc_beta; ep.use_enc = 1;
         enc_grad_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(ep);
         CUDA_OK(cudaGetLastError());
-        n_enc_rows = (int)(((B + 127) / 128) * 4) * ((ep.weik || ep.upz) ? 2 : 1);     // warps x sets, set-major
+        const int nsets = (ep.weik || ep.upz) ? 2 : 1;
+        const long long nwarps = ((B + 127) / 128) * 4;
+        enc_part = h->d_encrows + (size_t)2 * h->encrow_warps * kEncFloats;
+        enc_rows_partial_kernel<<<dim3((unsigned)((nsets * kEncFloats + 255) / 256), kEncChunks), 256, 0, st>>>(h->d_encrows, nwarps, nsets, enc_part);
+        CUDA_OK(cudaGetLastError());
+        n_enc_rows = kEncChunks * nsets;     // [set][chunk] rows, summed in this order by the reduce kernel
         h->launches++;
     }
     wgrad_reduce_kernel<<<(unsigned)((n_params + 255) / 256), 256, 0, st>>>(h->d_ws, ksplits, (long long)ws_stride, (long long)n_params,
-                                                                           h->cfg.use_enc ? kEncFloats : 0, h->d_encrows, n_enc_rows,
+                                                                           h->cfg.use_enc ? kEncFloats : 0, enc_part, n_enc_rows,
                                                                            grad_flat_dev, overwrite);
     CUDA_OK(cudaGetLastError());
     h->launches += 3;
@@ -1039,6 +1069,18 @@ int pndf_knn_exact(int device, const float* query_dev, int64_t Q, const float* d
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaFreeAsync(part_val, st));
     CUDA_OK(cudaFreeAsync(part_idx, st));
+    return 0;
+}
+
+int pndf_set_tile_policy(pndf_handle* h, int tile) {
+    if (!h) return fail("null handle");
+    if (tile != 0 && tile != 8 && tile != 32) return fail("pndf_set_tile_policy: tile must be 0 (auto), 8 or 32");
+    h->tile_policy = tile;
+    return 0;
+}
+int pndf_tile_for_batch(pndf_handle* h, int64_t B, int* tile) {
+    if (!h || !tile || B < 0) return fail("bad argument");
+    *tile = small_tile_for(h, B) ? 8 : 32;
     return 0;
 }
 

@@ -296,6 +296,22 @@ __global__ void __launch_bounds__(128) enc_grad_kernel(const EncTrainParams p) {
     }
 }
 
+// first level of the fixed-order reduction: part[set][chunk][i] = sum of rows[set][w][i] over the warps w of chunk
+// (chunk = blockIdx.y of kEncChunks); the second level (kEncChunks x sets rows) is folded into wgrad_reduce_kernel
+constexpr int kEncChunks = 16;
+__global__ void __launch_bounds__(256) enc_rows_partial_kernel(const float* __restrict__ rows, long long nwarps, int nsets,
+                                                              float* __restrict__ part) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsets * kEncFloats) return;
+    const int set = i / kEncFloats, e = i - set * kEncFloats;
+    const long long per = (nwarps + kEncChunks - 1) / kEncChunks;
+    const long long w0 = (long long)blockIdx.y * per, w1 = min(nwarps, w0 + per);
+    const float* r = rows + (size_t)set * nwarps * kEncFloats + e;
+    float s = 0.0f;
+    for (long long w = w0; w < w1; ++w) s += r[(size_t)w * kEncFloats];
+    part[((size_t)set * kEncChunks + blockIdx.y) * kEncFloats + e] = s;
+}
+
 // out[set][i] = sum over warps of rows[set][warp][i], fixed order
 __global__ void __launch_bounds__(256) enc_rows_reduce_kernel(const float* __restrict__ rows, long long nwarps, int nsets,
                                                              float* __restrict__ out) {

@@ -898,6 +898,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
     uint32_t aux_phase = 0;
     constexpr uint32_t kEncBytes = kEncFloats * 4;     // 14 064, a multiple of 16
     const bool keep = (MODE >= 1);
+    const bool bias_lane = !KS || c.kq == 0;      // KS: the four lane groups' partial sums are added up -- the bias goes into one of them
     EncLane enc;
     enc.l = lane & 7; enc.base = lane & 24; enc.m = warp * 4 + (lane >> 3);
     Pipe pipe;
@@ -1035,7 +1036,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             // ================================================================= forward
             {   // F0: z0 (X) -> z1 (Y), 256 wide
                 float acc[8][8];
-                if (c.kg == 0 && !tangent) acc_init_bias<8, 2>(acc, p.bias[0], c.ng2, 256); else acc_zero<8>(acc);
+                if (c.kg == 0 && !tangent && bias_lane) acc_init_bias<8, 2>(acc, p.bias[0], c.ng2, 256); else acc_zero<8>(acc);
                 gemm_op<8, 2, KS>(acc, X, p.f0_slabs, pipe, c); kq_reduce<8, KS>(acc);
                 splitk_combine<8, KS>(acc, Y, c);
                 if (c.kg == 0) { if (!tangent) epilogue_fwd<DSOFT, 8, 2, KS>(acc, Y, kU1, c, keep); else epilogue_bwd<DSOFT, 8, 2, KS>(acc, Y, kU1, c); }
@@ -1044,7 +1045,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             dump_rows(dbg_p, 128, Y, 256, tid);
             {   // F1: z1 (Y) -> z2 (X), 512 wide
                 float acc[8][8];
-                if (!tangent) acc_init_bias<8>(acc, p.bias[1], c.ng, 512); else acc_zero<8>(acc);
+                if (!tangent && bias_lane) acc_init_bias<8>(acc, p.bias[1], c.ng, 512); else acc_zero<8>(acc);
                 gemm_op<8, 1, KS>(acc, Y, kS1, pipe, c); kq_reduce<8, KS>(acc);
                 if (!tangent) epilogue_fwd<DSOFT, 8, 1, KS>(acc, X, kU2, c, keep); else epilogue_bwd<DSOFT, 8, 1, KS>(acc, X, kU2, c);
             }
@@ -1052,10 +1053,10 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             dump_rows(dbg_p, 384, X, 512, tid);
             {   // F2/F3 fused: z3 chunk (Y) is consumed at once as a K-chunk of layer 3; z4 -> X
                 float acc3[8][8];
-                if (!tangent) acc_init_bias<8>(acc3, p.bias[3], c.ng, 512); else acc_zero<8>(acc3);
+                if (!tangent && bias_lane) acc_init_bias<8>(acc3, p.bias[3], c.ng, 512); else acc_zero<8>(acc3);
                 for (int ch = 0; ch < 2; ++ch) {
                     float acc2[8][8];
-                    if (!tangent) acc_init_bias<8>(acc2, p.bias[2] + ch * 512, c.ng, 512); else acc_zero<8>(acc2);
+                    if (!tangent && bias_lane) acc_init_bias<8>(acc2, p.bias[2] + ch * 512, c.ng, 512); else acc_zero<8>(acc2);
                     gemm_op<8, 1, KS>(acc2, X, kS23, pipe, c); kq_reduce<8, KS>(acc2);
                     if (!tangent) epilogue_fwd<DSOFT, 8, 1, KS>(acc2, Y, kU3 + ch * 512, c, keep); else epilogue_bwd<DSOFT, 8, 1, KS>(acc2, Y, kU3 + ch * 512, c);
                     gemm_bar();
@@ -1070,7 +1071,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             dump_rows(dbg_p, 1920, X, 512, tid);
             {   // F4: z4 (X) -> z5 (Y), 256 wide
                 float acc[8][8];
-                if (c.kg == 0 && !tangent) acc_init_bias<8, 2>(acc, p.bias[4], c.ng2, 256); else acc_zero<8>(acc);
+                if (c.kg == 0 && !tangent && bias_lane) acc_init_bias<8, 2>(acc, p.bias[4], c.ng2, 256); else acc_zero<8>(acc);
                 gemm_op<8, 2, KS>(acc, X, kS4, pipe, c); kq_reduce<8, KS>(acc);
                 splitk_combine<8, KS>(acc, Y, c);
                 if (c.kg == 0) { if (!tangent) epilogue_fwd<DSOFT, 8, 2, KS>(acc, Y, kU5, c, keep); else epilogue_bwd<DSOFT, 8, 2, KS>(acc, Y, kU5, c); }
@@ -1079,7 +1080,7 @@ __global__ void __launch_bounds__(kThreads, 1) pndf_fused_kernel(const KParams p
             dump_rows(dbg_p, 2432, Y, 256, tid);
             {   // F5: z5 (Y) -> z6 (X), 64 wide
                 float acc[8][1];
-                if (!tangent) acc_init_bias<1>(acc, p.bias[5], c.ng, 64); else acc_zero<1>(acc);
+                if (!tangent && bias_lane) acc_init_bias<1>(acc, p.bias[5], c.ng, 64); else acc_zero<1>(acc);
                 gemm_op<1, 1, KS>(acc, Y, kS5, pipe, c); kq_reduce<1, KS>(acc);
                 if (!tangent) epilogue_fwd<DSOFT, 1, 1, KS>(acc, X, kU6, c, keep); else epilogue_bwd<DSOFT, 1, 1, KS>(acc, X, kU6, c);
             }

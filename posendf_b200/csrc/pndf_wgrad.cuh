@@ -28,7 +28,8 @@ constexpr int kWgTile = 128;          // output tile is kWgTile x kWgTile
 constexpr int kWgBK = 32;             // poses per pipeline stage
 constexpr int kWgStages = 2;
 constexpr int kWgThreads = 256;
-constexpr int kWgKC = 1024;           // poses per work item (one K-split)
+// poses per work item (one K-split): chosen per call by the host (multiple of kWgBK, ~1 000) so that the CTA count fills whole
+// waves of 2 CTAs per SM
 constexpr int kWgStageFloats = 3 * kWgBK * kWgTile;     // A | Z | Zdot
 constexpr int kWgSmem = kWgStages * kWgStageFloats * 4 + 64;
 constexpr int kWgMaxProblems = 6;
@@ -50,6 +51,7 @@ struct WgParams {
     float uniform;
     float* ws;               // workspace [slot][n_params]
     long long B, ws_stride;  // ws_stride = n_params rounded up to a multiple of 4 floats (16-byte aligned slots)
+    int kc;                  // poses per K-split (multiple of kWgBK)
     int slot0;               // this batch's first workspace slot; slot = slot0 + blockIdx.y
     int nprob;
     WgProblem prob[kWgMaxProblems];
@@ -85,8 +87,8 @@ __global__ void __launch_bounds__(kWgThreads, 2) wgrad_kernel(const WgParams p) 
     const WgProblem pr = p.prob[pi];
     const int t = blockIdx.x - pr.tile0;
     const int mt = t / pr.n_tiles, nt = t - mt * pr.n_tiles;
-    const long long k0 = (long long)blockIdx.y * kWgKC;
-    const long long kend = min(p.B, k0 + kWgKC);
+    const long long k0 = (long long)blockIdx.y * p.kc;
+    const long long kend = min(p.B, k0 + p.kc);
     const int nchunks = (int)((kend - k0 + kWgBK - 1) / kWgBK);
     const bool has_t = (p.dump_t != nullptr) && (p.w_eik != nullptr);
     const bool per_pose = (p.coef != nullptr);
@@ -234,7 +236,7 @@ struct WgLastParams {
     float uniform;
     float* ws;
     long long B, ws_stride, w6_off, b6_off;
-    int slot0, z6_col, softplus;
+    int kc, slot0, z6_col, softplus;
     float beta;
 };
 
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(256) wgrad_last_kernel(const WgLastParams p) {
     __shared__ float4 part[16][16];
     __shared__ float bpart[16];
     const int n4 = threadIdx.x & 15, kq = threadIdx.x >> 4;
-    const long long k0 = (long long)blockIdx.x * kWgKC, kend = min(p.B, k0 + kWgKC);
+    const long long k0 = (long long)blockIdx.x * p.kc, kend = min(p.B, k0 + p.kc);
     const bool has_t = (p.dump_t != nullptr) && (p.w_eik != nullptr);
     const float up = __ldg(p.up), we = has_t ? __ldg(p.w_eik) : 0.0f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);

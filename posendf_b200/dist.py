@@ -55,7 +55,12 @@ def project_sharded(net, poses: torch.Tensor, steps: int = 10, renorm: bool = Fa
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n = poses.reshape(-1, 21, 4).shape[0]
     lo, hi = shard_bounds(n, world, rank)
-    x, d = net.project(poses.reshape(-1, 21, 4)[lo:hi], steps=steps, renorm=renorm)
+    eng = net.engine()
+    eng.set_tile_policy(eng.tile_for_batch(n))       # the tiling of the WHOLE batch: sharded == unsharded bit for bit
+    try:
+        x, d = net.project(poses.reshape(-1, 21, 4)[lo:hi], steps=steps, renorm=renorm)
+    finally:
+        eng.set_tile_policy(0)
     return all_gather_ragged(x, n, group), all_gather_ragged(d, n, group)
 
 
@@ -127,8 +132,12 @@ class NcclGather:
         import posendf_b200._lib as _lib
         x = self.local_view()
         d = self.dist[self.rank * self.n:(self.rank + 1) * self.n]
-        _lib.check(eng.lib.pndf_project(eng._h, x.data_ptr(), self.n, int(steps), int(renorm), d.data_ptr(),
-                                        torch.cuda.current_stream(self.device).cuda_stream))
+        eng.set_tile_policy(eng.tile_for_batch(self.world * self.n))      # tiling of the whole batch (bit-identical to unsharded)
+        try:
+            _lib.check(eng.lib.pndf_project(eng._h, x.data_ptr(), self.n, int(steps), int(renorm), d.data_ptr(),
+                                            torch.cuda.current_stream(self.device).cuda_stream))
+        finally:
+            eng.set_tile_policy(0)
         dist.all_gather_into_tensor(self.poses, x, group=self.group)
         dist.all_gather_into_tensor(self.dist, d, group=self.group)
         return d
@@ -195,8 +204,12 @@ class PeerGather:
         x = self.local_view()
         d = self.dist[self.rank * self.n:(self.rank + 1) * self.n]
         st = torch.cuda.current_stream(self.device).cuda_stream
-        self._lib.check(self.lib.pndf_project_gather(eng._h, x.data_ptr(), self.n, int(steps), int(renorm), d.data_ptr(),
-                                                     self._peer_pose, self._peer_dist, self._npeers, st))
+        eng.set_tile_policy(eng.tile_for_batch(self.world * self.n))      # tiling of the whole batch (bit-identical to unsharded)
+        try:
+            self._lib.check(self.lib.pndf_project_gather(eng._h, x.data_ptr(), self.n, int(steps), int(renorm), d.data_ptr(),
+                                                         self._peer_pose, self._peer_dist, self._npeers, st))
+        finally:
+            eng.set_tile_policy(0)
         self.barrier()
         return d
 

@@ -137,6 +137,16 @@ class Engine:
                                                     dump.data_ptr(), _stream_ptr(self.device)))
         return dist, grad, dump
 
+    def tile_for_batch(self, B) -> int:
+        """tile size (8 or 32 poses) the library would pick for a batch of B poses"""
+        t = C.c_int()
+        _lib.check(self.lib.pndf_tile_for_batch(self._h, int(B), C.byref(t)))
+        return t.value
+
+    def set_tile_policy(self, tile=0):
+        """0 = per launch from its batch size; 8 / 32 = pinned (split batches that must match the unsplit run bit for bit)"""
+        _lib.check(self.lib.pndf_set_tile_policy(self._h, int(tile)))
+
     def launch_count(self) -> int:
         n = C.c_int64()
         _lib.check(self.lib.pndf_launch_count(self._h, C.byref(n)))
