@@ -265,7 +265,7 @@ def run_other_configs(eng, dev, rank, world, gather):
     ms = _max_over_ranks(a.elapsed_time(b) / n5, dev, world)
     out["C5_train_step"] = {"samples_per_gpu": B5, "manifold_samples_per_gpu": B5, "batch_total": world * B5, "ms_per_step": ms,
                             "samples_per_s": world * B5 / ms * 1e3, "optimizer": trainer.kind,
-                            "losses_rank0": {k: float(v) for k, v in ld.items()}}
+                            "losses_rank0": {k: float(v.detach()) for k, v in ld.items()}}
     return out
 
 
@@ -319,14 +319,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # the clock sampler (an nvidia-smi process polling every 100 ms) starts BEFORE the warm-up: its start-up must not fall into
+    # the timed region
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         x.copy_(x0)
+        flush.fill_(0)
         step()
     sync_all()
 
     # ---- timed region: exactly K steps, device time per step, L2 flushed between steps
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(_ev(), _ev()) for _ in range(args.steps)]
     launches0 = eng.launch_count()
     sync_all()
@@ -407,7 +410,7 @@ def main():
         line = {
             "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32", "data": "synthetic", "ms_steps_rank0": [round(t, 4) for t in ms],
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B,
                        "weights": "random-init amass.yaml, sensitised (SURVEY 8d)",
                        "l2": "256 MiB flush write between timed steps", "parallelism": f"pose-sharded x{world}",

@@ -1,6 +1,7 @@
 """Config C5 end to end: ONE epoch of the reference trainer loop (model/train_posendf.py:84-110 `train_model`) on
 synthetic data files in the reference's training format (data/prepare_traindata.py:173: npz {'pose','dist','nn_pose'}),
-fed by the device-resident loader, fused train step, gradient all-reduce across ranks, Adam(lr=1e-5, wd=1e-4).
+fed by the device-resident loader (pndf_feed_batch), native train step, ONE all-reduce of the flat gradient vector across ranks,
+FusedAdam(lr=1e-5, wd=1e-4) (posendf_b200.dist.DataParallelStep).
 
     python tools/train_epoch.py [--files 32] [--rows 20000] [--batch-size 8] [--num-pts 4096]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 tools/train_epoch.py
@@ -14,7 +15,7 @@ import numpy as np, torch
 import torch.distributed as dist
 from posendf_b200 import PoseNDF, synth
 from posendf_b200.data import ResidentPoseData
-from posendf_b200.dist import allreduce_gradients
+from posendf_b200.dist import DataParallelStep
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--files", type=int, default=32, help="data files per rank (one item each, load_data.py:43)")
@@ -52,26 +53,20 @@ opt = {"train": {"device": f"cuda:{local}", "loss_type": "l1", "batch_size": arg
 net = PoseNDF(opt)
 net.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_params(1).items()})
 net.train()
-optim = torch.optim.Adam(net.parameters(), lr=1e-5, weight_decay=1e-4)      # train_posendf.py:30
-loss_weight = {"man_loss": 1.0, "dist": 1.0, "eikonal": 1.0}                 # configs/amass.yaml:56-58
+# train_posendf.py:30 Adam(lr, weight_decay=1e-4) as the fused optimizer kernel; configs/amass.yaml:56-58 loss weights 1 / 1 / 1
+trainer = DataParallelStep(net, lr=1e-5, weight_decay=1e-4, weights=(1.0, 1.0, 1.0))
 
 
 def epoch():
     tot, n = torch.zeros((), device=dev), 0
-    for inputs in loader:                                                     # train_posendf.py:89-99
-        optim.zero_grad()
-        _, ld = net(inputs["pose"], inputs["dist"], inputs["man_poses"], eikonal=loss_weight["eikonal"])
-        loss = sum(loss_weight[k] * ld[k] for k in ld)
-        loss.backward()
-        if world > 1:
-            allreduce_gradients(net)
-        optim.step()
-        tot += loss.detach()
+    for inputs in loader:                                                     # train_posendf.py:89-99, one feed-kernel launch per batch
+        ld = trainer.step(inputs["pose"], inputs["dist"], inputs["man_poses"])
+        tot += sum(v.detach() for v in ld.values())
         n += 1
     return tot / max(n, 1), n
 
 
-epoch()                                                                       # warm-up epoch (allocator, cuBLAS heuristics)
+epoch()                                                                       # warm-up epoch (allocator)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
