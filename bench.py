@@ -238,7 +238,8 @@ def run_other_configs(eng, dev, rank, world, gather):
     sync(); a.record(); eng.denoise_prior_(aa, iterations=2, steps_per_iter=50); b.record(); sync()
     ms = _max_over_ranks(a.elapsed_time(b), dev, world)
     out["C4_denoise_100_adam_steps"] = {"sequences_per_gpu": S, "frames": T, "steps": 100, "ms": ms,
-                                        "kernel_launches_per_gpu": int(eng.launch_count() - l0),
+                                        "kernel_launches_per_gpu": int(eng.launch_count() - l0), "graph_launches_per_gpu": 1,
+                                        "note": "two sequence groups = two parallel launch chains inside ONE CUDA graph",
                                         "pose_steps_per_s": world * S * T * 100 / ms * 1e3, "sequences_per_s": world * S / ms * 1e3}
     del aa, aa0
 

@@ -136,9 +136,10 @@ int pndf_prior_grad(pndf_handle* h, const float* aa_dev, int64_t B, const float*
  * distances of the last evaluated step.  loss_hist_dev (iterations*steps_per_iter*S floats, may be NULL): the
  * weighted prior loss per step and sequence.  ONE launch per step: the fused prior kernel of step t applies, in its tile
  * prologue, the Adam update step t-1 asked for (the per-sequence mean of dist couples the tiles of a sequence, so it is read
- * back from the previous launch's distances); a small per-sequence kernel applies the last update.  The steps_total + 1
- * launches are captured into a CUDA graph and replayed as one graph launch on `stream` (PNDF_NO_GRAPH=1 in the environment:
- * plain launches).  The SMPL temporal / data terms need licensed SMPL files and are out of scope. */
+ * back from the previous launch's distances); a small per-sequence kernel applies the last update.  Sequences are independent,
+ * so they run as two groups with their own launch chains side by side (the tail round of one group's launch overlaps the other
+ * group's next launch).  The 2 x (steps_total + 1) launches are captured into a CUDA graph and replayed as one graph launch on
+ * `stream` (PNDF_NO_GRAPH=1 in the environment: plain launches on `stream` and one internal stream).  The SMPL temporal / data terms need licensed SMPL files and are out of scope. */
 int pndf_denoise_prior(pndf_handle* h, float* aa_dev, int64_t S, int64_t T, int iterations, int steps_per_iter, float lr,
                        float* dist_dev, float* loss_hist_dev, void* stream);
 

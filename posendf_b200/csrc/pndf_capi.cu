@@ -93,6 +93,8 @@ struct pndf_handle {
     float* d_dn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // + second distance buffer
     int64_t dn_poses = 0;
     cudaStream_t cap_stream = nullptr;   // graph capture of the denoise loop
+    cudaStream_t dn_stream2 = nullptr;   // second sequence group of the denoise loop (parallel branch)
+    cudaEvent_t dn_ev[2] = {nullptr, nullptr};
     cudaGraphExec_t dn_exec = nullptr;
     bool in_capture = false;
     int tile_policy = 0;                 // 0: per launch from its batch size (use_small_tile), 8 / 32: pinned (pndf_set_tile_policy)
@@ -425,6 +427,9 @@ int pndf_destroy(pndf_handle* h) {
     for (int i = 0; i < 5; ++i) cudaFree(h->d_dn[i]);
     if (h->dn_exec) cudaGraphExecDestroy(h->dn_exec);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->dn_stream2) cudaStreamDestroy(h->dn_stream2);
+    for (int i = 0; i < 2; ++i)
+        if (h->dn_ev[i]) cudaEventDestroy(h->dn_ev[i]);
     for (int i = 0; i < 3; ++i) cudaFree(h->d_pos[i]);
     cudaFree(h->d_ws);
     cudaFree(h->d_encrows);
@@ -634,6 +639,16 @@ int pndf_denoise_prior(pndf_handle* h, float* aa_dev, int64_t S, int64_t T, int 
         for (int i = 3; i < 5; ++i) CUDA_OK(cudaMalloc(&h->d_dn[i], (size_t)B * sizeof(float)));
         h->dn_poses = B;
     }
+    if (!h->dn_stream2) {
+        if (cudaStreamCreateWithFlags(&h->dn_stream2, cudaStreamNonBlocking) != cudaSuccess) h->dn_stream2 = nullptr;
+        for (int i = 0; i < 2 && h->dn_stream2; ++i)
+            if (cudaEventCreateWithFlags(&h->dn_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+                cudaStreamDestroy(h->dn_stream2);
+                h->dn_stream2 = nullptr;
+            }
+        cudaGetLastError();
+    }
+    if (h->dn_stream2 && ensure_slot(h, 1)) return 1;
     float* graw = h->d_dn[0];
     float* m = h->d_dn[1];
     float* v = h->d_dn[2];
@@ -649,27 +664,50 @@ int pndf_denoise_prior(pndf_handle* h, float* aa_dev, int64_t S, int64_t T, int 
         ap.weight = 1e7f / (1.0f + (float)it);
         return ap;
     };
-    // ONE launch per optimisation step (prior + gradient, with the previous step's Adam update fused into its prologue) and one
-    // trailing update kernel; the whole loop is captured into a CUDA graph and replayed as a single graph launch
-    auto enqueue = [&](cudaStream_t s) -> int {
-        if (cudaMemsetAsync(m, 0, (size_t)B * 63 * sizeof(float), s) != cudaSuccess) return fail("cudaMemsetAsync failed");
-        if (cudaMemsetAsync(v, 0, (size_t)B * 63 * sizeof(float), s) != cudaSuccess) return fail("cudaMemsetAsync failed");
-        for (int t = 0; t < nsteps; ++t) {
-            KParams p{};
-            p.pose_in = aa_dev; p.dist = dbuf[(nsteps - 1 - t) & 1]; p.grad = graw; p.B = B; p.steps = 1; p.normalise = 1;
-            p.input_kind = IN_AXIS_ANGLE;
-            if (t > 0) {
-                p.dn.pending = 1; p.dn.m = m; p.dn.v = v; p.dn.graw = graw; p.dn.dist_prev = dbuf[(nsteps - t) & 1];
-                p.dn.pose_rw = aa_dev; p.dn.T = (int)T; p.dn.ap = adam_of(t, (t - 1) / steps_per_iter);
-                p.dn.loss_out = loss_hist_dev ? loss_hist_dev + (size_t)(t - 1) * S : nullptr;
-            }
-            if (launch(h, p, 1, s)) return 1;
+    // ONE launch per optimisation step and sequence group (prior + gradient, with the previous step's Adam update fused into its
+    // prologue) and one trailing update kernel per group; the whole loop is captured into a CUDA graph and replayed as a single
+    // graph launch.  Sequences are independent of each other, so they are split into two groups whose launch chains run side by
+    // side (second internal stream = a parallel branch of the graph, its own per-CTA scratch slot): when the persistent CTAs of
+    // one group's launch run out of tiles, the other group's next launch takes over their SMs -- without it 1 200 tiles on 148
+    // SMs (config C4) leave the ninth round 90 % empty in every one of the 100 steps.
+    const int G = (S >= 2 && h->dn_stream2 != nullptr) ? 2 : 1;
+    auto enqueue = [&](cudaStream_t s0) -> int {
+        if (cudaMemsetAsync(m, 0, (size_t)B * 63 * sizeof(float), s0) != cudaSuccess) return fail("cudaMemsetAsync failed");
+        if (cudaMemsetAsync(v, 0, (size_t)B * 63 * sizeof(float), s0) != cudaSuccess) return fail("cudaMemsetAsync failed");
+        cudaStream_t sg[2] = {s0, h->dn_stream2};
+        const int64_t seq0[3] = {0, G == 2 ? S / 2 : S, S};
+        if (G == 2) {
+            if (cudaEventRecord(h->dn_ev[0], s0) != cudaSuccess || cudaStreamWaitEvent(sg[1], h->dn_ev[0], 0) != cudaSuccess)
+                return fail("denoise: fork failed");
         }
-        seq_adam_kernel<<<(unsigned)S, 256, 0, s>>>(aa_dev, graw, dbuf[0], m, v,
-                                                    loss_hist_dev ? loss_hist_dev + (size_t)(nsteps - 1) * S : nullptr, (int)T,
-                                                    adam_of(nsteps, (nsteps - 1) / steps_per_iter));
-        if (cudaGetLastError() != cudaSuccess) return fail("seq_adam_kernel launch failed");
-        h->launches++;
+        for (int t = 0; t < nsteps; ++t) {
+            for (int g = 0; g < G; ++g) {
+                const int64_t o = seq0[g] * T, Bg = (seq0[g + 1] - seq0[g]) * T;      // first pose / poses of the group
+                KParams p{};
+                p.pose_in = aa_dev + o * 63; p.dist = dbuf[(nsteps - 1 - t) & 1] + o; p.grad = graw + o * 63; p.B = Bg; p.steps = 1;
+                p.normalise = 1; p.input_kind = IN_AXIS_ANGLE;
+                if (t > 0) {
+                    p.dn.pending = 1; p.dn.m = m + o * 63; p.dn.v = v + o * 63; p.dn.graw = graw + o * 63;
+                    p.dn.dist_prev = dbuf[(nsteps - t) & 1] + o; p.dn.pose_rw = aa_dev + o * 63; p.dn.T = (int)T;
+                    p.dn.ap = adam_of(t, (t - 1) / steps_per_iter);
+                    p.dn.loss_out = loss_hist_dev ? loss_hist_dev + (size_t)(t - 1) * S + seq0[g] : nullptr;
+                }
+                if (launch(h, p, 1, sg[g], g)) return 1;
+            }
+        }
+        for (int g = 0; g < G; ++g) {
+            const int64_t o = seq0[g] * T;
+            seq_adam_kernel<<<(unsigned)(seq0[g + 1] - seq0[g]), 256, 0, sg[g]>>>(
+                aa_dev + o * 63, graw + o * 63, dbuf[0] + o, m + o * 63, v + o * 63,
+                loss_hist_dev ? loss_hist_dev + (size_t)(nsteps - 1) * S + seq0[g] : nullptr, (int)T,
+                adam_of(nsteps, (nsteps - 1) / steps_per_iter));
+            if (cudaGetLastError() != cudaSuccess) return fail("seq_adam_kernel launch failed");
+            h->launches++;
+        }
+        if (G == 2) {
+            if (cudaEventRecord(h->dn_ev[1], sg[1]) != cudaSuccess || cudaStreamWaitEvent(s0, h->dn_ev[1], 0) != cudaSuccess)
+                return fail("denoise: join failed");
+        }
         return 0;
     };
     if (order_after_weights(h, st)) return 1;
