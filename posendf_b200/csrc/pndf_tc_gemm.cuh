@@ -1,0 +1,236 @@
+// pndf_tc_gemm.cuh -- 3xTF32 GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), the building block of the tensor-core
+// DFNet path.
+//
+//     D[M x N] = epilogue( A[M x K] * B[N x K]^T )        A, B given as tf32 hi / lo pairs (x = hi + lo, both exactly
+//                                                          representable in tf32), row-major, K contiguous (K-major)
+//
+// Arithmetic (measured to hold the 1e-5 parity bar of the whole DFNet chain, tools/tc_chain_probe.cu):
+//     A*B ~= A_hi B_hi  +  (A_lo B_hi + A_hi B_lo)     three tcgen05.mma.kind::tf32 per K step, the big term and the cross
+// terms in SEPARATE TMEM accumulators, a fresh accumulator pair per 128-deep K chunk; pairs are added in fp32 (round to nearest)
+// on the CUDA cores -- the tensor core's accumulator truncates, so the long sum must not live in it.
+//
+// One CTA = one 128 x NT output tile (NT = 128 or 64), 192 threads, warp-specialised:
+//   warp 0      TMA producer: per 32-deep K stage four tile loads (A_hi, A_lo 128 x 32, B_hi, B_lo NT x 32, SWIZZLE_128B) on a
+//               `full` mbarrier; 3 stages in flight
+//   warp 1      MMA issuer (one lane): 12 MMAs per stage; tcgen05.commit releases the stage (`empty`) and, at the end of a K chunk,
+//               publishes the accumulator pair (`acc_full`)
+//   warps 2-5   drain: tcgen05.ld both accumulators of the finished pair, add into 128 running fp32 sums per thread (thread = one
+//               output row = one TMEM lane), hand the pair back (`acc_empty`) so that the next-but-one chunk can overwrite it --
+//               the drain of chunk c runs under the MMAs of chunk c+1 (two pairs = 4 x NT TMEM columns); finally the epilogue
+//               functor turns the 128-float row segment into whatever the layer needs.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pndf_tc {
+
+constexpr int kTM = 128;                 // rows (poses) per tile = TMEM lanes
+constexpr int kKB = 32;                  // K per stage = one 128-byte swizzle row of tf32
+constexpr int kStages = 3;
+constexpr int kChunkK = 128;             // K depth per accumulator pair
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (++spins > (1u << 26)) __trap();      // a lost arrival is a launch error, never a hung GPU
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row x 128-byte atoms, 1024 bytes apart)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
+template <int NT>
+__host__ __device__ constexpr int stage_bytes() { return 2 * kTM * 128 + 2 * NT * 128; }
+template <int NT>
+__host__ __device__ constexpr int smem_bytes() { return kStages * stage_bytes<NT>() + 1024 + 256; }
+
+struct GemmMaps {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+
+// Epilogue functor interface: void operator()(int row /*global*/, int col0 /*global, multiple of 32*/, float (&v)[32]) -- called by
+// the thread that owns `row` for every 32-column group of its tile.
+template <int NT, class Epilogue>
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmMaps maps, int K, Epilogue epi) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes<NT>());
+    uint64_t* full = bars;                   // [kStages]
+    uint64_t* empty = bars + kStages;        // [kStages]
+    uint64_t* acc_full = bars + 2 * kStages; // [2]
+    uint64_t* acc_empty = acc_full + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * NT, m0 = blockIdx.y * kTM;
+    const int nks = K / kKB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int p = 0; p < 2; ++p) { mbar_init(&acc_full[p], 1); mbar_init(&acc_empty[p], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(4 * NT < 32 ? 32 : 4 * NT));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            for (int ks = 0; ks < nks; ++ks) {
+                const int s = ks % kStages;
+                mbar_wait(&empty[s], ((ks / kStages) & 1) ^ 1);      // fresh barrier: parity 1 passes
+                uint8_t* st = smem + s * stage_bytes<NT>();
+                mbar_expect_tx(&full[s], stage_bytes<NT>());
+                tma_load_2d(st, &maps.a_hi, ks * kKB, m0, &full[s]);
+                tma_load_2d(st + kTM * 128, &maps.a_lo, ks * kKB, m0, &full[s]);
+                tma_load_2d(st + 2 * kTM * 128, &maps.b_hi, ks * kKB, n0, &full[s]);
+                tma_load_2d(st + 2 * kTM * 128 + NT * 128, &maps.b_lo, ks * kKB, n0, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            // D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+            constexpr int kStagesPerChunk = kChunkK / kKB;
+            for (int ks = 0; ks < nks; ++ks) {
+                const int s = ks % kStages, c = ks / kStagesPerChunk, p = c & 1;
+                const bool chunk_start = (ks % kStagesPerChunk) == 0;
+                if (chunk_start) mbar_wait(&acc_empty[p], ((c >> 1) & 1) ^ 1);      // the drain of chunk c-2 has emptied pair p
+                mbar_wait(&full[s], (ks / kStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t st = smem_u32(smem + s * stage_bytes<NT>());
+                const uint32_t a_hi = st, a_lo = st + kTM * 128, b_hi = st + 2 * kTM * 128, b_lo = b_hi + NT * 128;
+                const uint32_t acc_hh = tmem + (uint32_t)(p * 2 * NT), acc_x = acc_hh + NT;
+#pragma unroll
+                for (int k = 0; k < kKB / 8; ++k) {
+                    const uint32_t first = (chunk_start && k == 0) ? 0u : 1u;
+                    mma_tf32(acc_hh, make_desc(a_hi + k * 32), make_desc(b_hi + k * 32), idesc, first);
+                    mma_tf32(acc_x, make_desc(a_lo + k * 32), make_desc(b_hi + k * 32), idesc, first);
+                    mma_tf32(acc_x, make_desc(a_hi + k * 32), make_desc(b_lo + k * 32), idesc, 1u);
+                }
+                mma_commit(&empty[s]);                                               // stage s may be refilled once these MMAs retire
+                if ((ks % kStagesPerChunk) == kStagesPerChunk - 1 || ks == nks - 1) mma_commit(&acc_full[p]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ drain + epilogue: thread = output row
+        const int quarter = warp & 3;                       // TMEM lanes [32 q, 32 q + 32) are this warp's
+        const int row = m0 + quarter * 32 + lane;
+        float run[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) run[j] = 0.0f;
+        const int nchunks = (K + kChunkK - 1) / kChunkK;
+        for (int c = 0; c < nchunks; ++c) {
+            const int p = c & 1;
+            mbar_wait(&acc_full[p], (c >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const uint32_t base = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p * 2 * NT);
+#pragma unroll
+            for (int g = 0; g < NT / 32; ++g) {
+                uint32_t hh[32], xx[32];
+                tmem_ld32(base + g * 32, hh);
+                tmem_ld32(base + NT + g * 32, xx);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) run[g * 32 + j] += __uint_as_float(hh[j]) + __uint_as_float(xx[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[p]);
+        }
+#pragma unroll
+        for (int g = 0; g < NT / 32; ++g) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = run[g * 32 + j];
+            epi(row, n0 + g * 32, v);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(4 * NT < 32 ? 32 : 4 * NT));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// fp32 row-major matrix [rows][ld] (K contiguous, ld >= K, ld * 4 a multiple of 16): boxes of `box_rows` rows x 32 columns, 128B swizzle
+inline bool make_map(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {K, rows};
+    const cuuint64_t strides[1] = {ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kKB, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace pndf_tc
