@@ -7,6 +7,7 @@
 #include "pndf_train_ops.cuh"
 #include "pndf_wgrad.cuh"
 #include "pndf_feed.cuh"
+#include "pndf_tc.h"
 #include "pndf_knn.cuh"
 
 #include <algorithm>
@@ -43,6 +44,7 @@ int fail(const std::string& msg) {
 
 const int kAmassDims[6] = {256, 512, 1024, 512, 256, 64};
 const double kSmallTileCost = 0.40;      // time of an 8-pose tile relative to a 32-pose tile (measured)
+const long long kTcMinBatch = 16384;     // from this batch size on the DFNet GEMMs run on the tensor cores (pndf_tc.cu)
 
 }  // namespace
 
@@ -97,7 +99,8 @@ struct pndf_handle {
     cudaEvent_t dn_ev[2] = {nullptr, nullptr};
     cudaGraphExec_t dn_exec = nullptr;
     bool in_capture = false;
-    int tile_policy = 0;                 // 0: per launch from its batch size (use_small_tile), 8 / 32: pinned (pndf_set_tile_policy)
+    int tile_policy = 0;                 // 0: per launch from its batch size, 8 / 32 / 128: pinned (pndf_set_tile_policy); 128 = tensor-core path
+    TcState* tc = nullptr;               // tensor-core DFNet path (pndf_tc.cu); nullptr if it could not be set up
 };
 
 namespace {
@@ -227,6 +230,7 @@ int pack_on_device(pndf_handle* h, const float* d_flat, cudaStream_t st) {
     pack_gather_kernel<<<h->num_sms * 4, 256, 0, st>>>(d_flat, h->d_map_w, h->d_wstream, h->wstream_floats);
     pack_gather_kernel<<<8, 256, 0, st>>>(d_flat, h->d_map_s, h->d_small, h->small_floats);
     CUDA_OK(cudaGetLastError());
+    if (h->tc && tc_set_weights(h->tc, d_flat, st)) return fail(std::string("tensor-core path: ") + tc_last_error(h->tc));
     if (!h->w_event) CUDA_OK(cudaEventCreateWithFlags(&h->w_event, cudaEventDisableTiming));
     CUDA_OK(cudaEventRecord(h->w_event, st));
     h->w_stream = st;
@@ -325,6 +329,17 @@ bool use_small_tile(const pndf_handle* h, const KParams& p, int mode) {
     if (h->tile_policy != 0) return h->tile_policy == 8;
     return small_tile_for(h, p.B);
 }
+// Large batches of plain quaternion poses (forward, forward + gradient, projection steps) take the tensor-core path: the DFNet
+// GEMMs as 3xTF32 tcgen05 kernels, ~2x the FFMA kernel.  Everything else (axis-angle prior / denoise loop, training
+// exports, debug dump, small batches) stays on the fused FFMA kernel.
+bool use_tc(const pndf_handle* h, const KParams& p, int mode) {
+    if (!h->tc || mode == 2 || p.dbg != nullptr || p.act_masks != nullptr || p.tan_in != nullptr || p.input_kind != IN_QUAT ||
+        p.dn.pending != 0 || (mode == 1 && p.steps > 1 && p.pose_out == nullptr))
+        return false;
+    if (const char* e = getenv("PNDF_TILE")) return atoi(e) == 128;
+    if (h->tile_policy != 0) return h->tile_policy == 128;
+    return p.B >= kTcMinBatch;
+}
 
 int ensure_slot(pndf_handle* h, int slot) {
     if (!h->d_z0[slot]) CUDA_OK(cudaMalloc(&h->d_z0[slot], (size_t)h->num_sms * 128 * 32 * sizeof(float)));
@@ -354,6 +369,21 @@ int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st, int slot = 0) 
     p.encw = h->cfg.use_enc ? h->d_small + h->off_enc : nullptr;
     p.dscratch = h->d_scratch[slot];
     p.z0scratch = h->d_z0[slot];
+    if (use_tc(h, p, mode)) {
+        TcArgs a;
+        a.pose_in = p.pose_in; a.pose_out = p.pose_out; a.dist = p.dist; a.grad = p.grad; a.g_up = p.g_up; a.B = p.B;
+        a.steps = p.steps; a.do_step = p.do_step; a.renorm = p.renorm; a.normalise = p.normalise; a.want_grad = (mode == 1);
+        a.encw = p.encw; a.w6 = p.w6; a.n_peers = p.n_peers;
+        for (int l = 0; l < 7; ++l) a.bias[l] = p.bias[l];
+        for (int r = 0; r < p.n_peers; ++r) { a.peer_pose[r] = p.peer_pose[r]; a.peer_dist[r] = p.peer_dist[r]; }
+        if (!h->in_capture && order_after_weights(h, st)) return 1;
+        if (tc_run(h->tc, a, st, &h->launches)) return fail(std::string("tensor-core path: ") + tc_last_error(h->tc));
+        if (h->in_capture) return 0;
+        CUDA_OK(cudaEventRecord(h->use_event, st));
+        h->use_stream = st;
+        h->used = true;
+        return 0;
+    }
     const bool small = use_small_tile(h, p, mode);
     p.ntiles = (int)(small ? (p.B + 7) / 8 : (p.B + kTileM - 1) / kTileM);
     p.use_enc = h->cfg.use_enc; p.enc_act = h->cfg.enc_act; p.df_act = h->cfg.df_act;
@@ -406,6 +436,7 @@ int pndf_create(const pndf_config* cfg, pndf_handle** out) {
     if (ensure_slot(h, 0)) { pndf_destroy(h); return 1; }
     if (cudaEventCreateWithFlags(&h->use_event, cudaEventDisableTiming) != cudaSuccess) { pndf_destroy(h); return fail("cudaEventCreate failed"); }
     if (build_maps(h)) { pndf_destroy(h); return 1; }
+    if (tc_create(&h->tc, cfg)) { h->tc = nullptr; cudaGetLastError(); }      // without it everything runs on the FFMA kernels
     *out = h;
     return 0;
 }
@@ -420,6 +451,7 @@ int pndf_destroy(pndf_handle* h) {
     cudaFree(h->d_flat);
     if (h->w_event) cudaEventDestroy(h->w_event);
     if (h->use_event) cudaEventDestroy(h->use_event);
+    tc_destroy(h->tc);
     for (int i = 0; i < 3; ++i) {
         cudaFree(h->d_scratch[i]);
         cudaFree(h->d_z0[i]);
@@ -600,7 +632,7 @@ int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out
     if (ensure_slot(h, 1) || ensure_slot(h, 2)) return 1;   // the two streams overlap: each needs its own per-CTA scratch
     // one tile size for all chunks, the one the whole batch would get: the result equals pndf_project on the same batch bit for bit
     const int saved_policy = h->tile_policy;
-    if (saved_policy == 0) h->tile_policy = small_tile_for(h, B) ? 8 : 32;
+    if (saved_policy == 0) h->tile_policy = (h->tc && B >= kTcMinBatch) ? 128 : (small_tile_for(h, B) ? 8 : 32);
     struct Restore { pndf_handle* h; int v; ~Restore() { h->tile_policy = v; } } restore{h, saved_policy};
     int which = 0;
     for (int64_t off = 0; off < B; off += chunk, which ^= 1) {
@@ -1001,6 +1033,7 @@ int pndf_adam_step(pndf_handle* h, float* param_flat_dev, const float* grad_flat
     p.pos_a = h->d_pos[0]; p.pos_b = h->d_pos[1]; p.pos_s = h->d_pos[2]; p.wstream = h->d_wstream; p.small = h->d_small;
     adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
     CUDA_OK(cudaGetLastError());
+    if (h->tc && tc_set_weights(h->tc, param_flat_dev, st)) return fail(std::string("tensor-core path: ") + tc_last_error(h->tc));
     if (!h->w_event) CUDA_OK(cudaEventCreateWithFlags(&h->w_event, cudaEventDisableTiming));
     CUDA_OK(cudaEventRecord(h->w_event, st));
     h->w_stream = st;
@@ -1112,13 +1145,14 @@ int pndf_knn_exact(int device, const float* query_dev, int64_t Q, const float* d
 
 int pndf_set_tile_policy(pndf_handle* h, int tile) {
     if (!h) return fail("null handle");
-    if (tile != 0 && tile != 8 && tile != 32) return fail("pndf_set_tile_policy: tile must be 0 (auto), 8 or 32");
+    if (tile != 0 && tile != 8 && tile != 32 && tile != 128) return fail("pndf_set_tile_policy: tile must be 0 (auto), 8, 32 or 128");
+    if (tile == 128 && !h->tc) return fail("pndf_set_tile_policy: the tensor-core path is not available on this handle");
     h->tile_policy = tile;
     return 0;
 }
 int pndf_tile_for_batch(pndf_handle* h, int64_t B, int* tile) {
     if (!h || !tile || B < 0) return fail("bad argument");
-    *tile = small_tile_for(h, B) ? 8 : 32;
+    *tile = (h->tc && B >= kTcMinBatch) ? 128 : (small_tile_for(h, B) ? 8 : 32);
     return 0;
 }
 

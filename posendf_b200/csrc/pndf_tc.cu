@@ -1,0 +1,543 @@
+// pndf_tc.cu -- the tensor-core DFNet path: PoseNDF distance, its analytic gradient and the projection step for LARGE batches with
+// the seven DFNet layers (99.8 % of the flops) on the 5th-gen tensor cores.
+//
+// Reference semantics: PoseNDF.forward(train=False) + gradient() + the projection step, model/posendf.py:62-76,100-101,18-27 and
+// experiments/sample_poses.py:70-74 -- identical to the FFMA kernel's (pndf_kernel.cuh); only where the DFNet GEMMs run changes.
+//
+// One projection step of B poses is a sequence of launches on one stream:
+//   tc_enc_fwd_kernel     32-pose tiles: column normalise, structure encoder along the kinematic tree (the same device code as the
+//                         fused kernel, 8 lanes per pose) -> z0 as tf32 hi / lo pairs, pose-major [pose][128]
+//   6 x tc_gemm_kernel    z_{l+1} = act(z_l W_l^T + b_l): 3xTF32 tcgen05 GEMM (pndf_tc_gemm.cuh), epilogue = bias + activation +
+//                         hi / lo split, activations stay pose-major in HBM / L2 (43 KB per pose for the whole chain)
+//   tc_head_kernel        layer 6 (64 -> 1), output activation, dist; seeds the reverse chain t_5 = g_up phi_out'(s) w_6 phi'(pre_5)
+//   6 x tc_gemm_kernel    t_{l-1} = (t_l W_l) * phi'(pre_{l-1}): the same GEMM on the transposed weight copies, epilogue multiplies
+//                         by the activation derivative recovered from the stored activation z_l (sign for relu / lrelu,
+//                         1 - exp(-beta z) for softplus); the last one leaves g0 = dd/dz0 in fp32
+//   tc_enc_bwd_kernel     32-pose tiles: encoder forward again (cheaper than storing its intermediates), encoder reverse sweep,
+//                         Jacobian of the column normalisation, x <- x - d * g, optional renormalisation, write-back (+ the fused
+//                         gather: the same values to every peer GPU's gathered buffer)
+// K-step projections repeat the sequence K times (the FFMA kernel keeps the tile on chip instead; here the step is 2x faster).
+//
+// Numerics: tools/tc_chain_probe.cu measured the chain (split accumulators + 128-deep K chunks) at the accuracy of the fp32 FMA
+// chain; tests/test_gpu_parity.py runs the golden / oracle comparisons on this path too (tile policy 128).
+#include "pndf_tc.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "pndf_kernel.cuh"
+#include "pndf_tc_gemm.cuh"
+
+namespace pndf {
+
+namespace {
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+// ---- GEMM epilogues (called by the thread owning output row `row` for each 32-column group; the kernel stores the outputs)
+struct FwdEpi {          // z = act(acc + bias) -> hi / lo
+    static constexpr int kOutputs = 2;
+    const float* bias;
+    float* out_hi;
+    float* out_lo;
+    int ldo, soft;
+    float par;           // slope (relu 0 / lrelu 0.01) or softplus beta
+    __device__ float* out(int w) const { return w == 0 ? out_hi : out_lo; }
+    __device__ int ld() const { return ldo; }
+    __device__ void operator()(int row, int col0, const float (&v)[32], float (&hi)[32], float (&lo)[32]) const {
+        const float inv_beta = soft ? 1.0f / par : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float x = v[j] + __ldg(bias + col0 + j);
+            float dv;
+            const float z = soft ? softplus_fast(x, par, inv_beta, dv) : (x > 0.0f ? x : x * par);
+            hi[j] = tf32_rna(z);
+            lo[j] = tf32_rna(z - hi[j]);
+        }
+    }
+};
+struct BwdEpi {          // t = acc * act'(pre) with act' recovered from the stored activation z -> hi / lo
+    static constexpr int kOutputs = 2;
+    const float* z_hi;
+    const float* z_lo;
+    float* out_hi;
+    float* out_lo;
+    int ldo, soft;
+    float par;
+    __device__ float* out(int w) const { return w == 0 ? out_hi : out_lo; }
+    __device__ int ld() const { return ldo; }
+    __device__ void operator()(int row, int col0, const float (&v)[32], float (&hi)[32], float (&lo)[32]) const {
+        const size_t off = pndf_tc::tiled_offset(row, col0, ldo);      // 32 contiguous floats (all operands are in the tiled layout)
+        const float4* zh = reinterpret_cast<const float4*>(z_hi + off);
+        const float4* zl = reinterpret_cast<const float4*>(z_lo + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 a = __ldg(zh + j);
+            float zz[4] = {a.x, a.y, a.z, a.w};
+            if (soft) {
+                const float4 b = __ldg(zl + j);
+                zz[0] += b.x; zz[1] += b.y; zz[2] += b.z; zz[3] += b.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float d = soft ? -expm1f(-par * zz[k]) : (zz[k] > 0.0f ? 1.0f : par);
+                const float t = v[4 * j + k] * d;
+                hi[4 * j + k] = tf32_rna(t);
+                lo[4 * j + k] = tf32_rna(t - hi[4 * j + k]);
+            }
+        }
+    }
+};
+struct G0Epi {           // the last reverse op: dd/dz0 in fp32
+    static constexpr int kOutputs = 1;
+    float* o;
+    int ldo;
+    __device__ float* out(int) const { return o; }
+    __device__ int ld() const { return ldo; }
+    __device__ void operator()(int, int, const float (&v)[32], float (&o0)[32], float (&)[32]) const {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o0[j] = v[j];
+    }
+};
+
+// ---- weights: flat fp32 parameter vector -> tf32 hi / lo copies, forward layout W_l [n_out][k_pad] and reverse layout W_l^T [n_in_pad][n_out]
+struct SplitParams {
+    const float* flat;
+    float* hi;
+    float* lo;
+    long long w_off[6];      // offset of W_l in the flat vector
+    long long f_off[6];      // offset of the forward copy of layer l in hi / lo
+    long long r_off[6];      // offset of the reverse copy
+    int n_in[6], n_out[6], k_pad[6], n_in_pad[6];
+    int f_tile[6];           // row tile of the forward copy (= the N tile of its GEMM: 128, 64 for the 64-wide layer)
+    long long total;
+};
+__global__ void __launch_bounds__(256) tc_split_weights_kernel(const SplitParams p) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total; i += (long long)gridDim.x * blockDim.x) {
+        int l = 0;
+        bool rev = false;
+        long long base = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (i >= p.f_off[k]) { l = k; rev = false; base = p.f_off[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (i >= p.r_off[k]) { l = k; rev = true; base = p.r_off[k]; }
+        }
+        // element e of a TILED [rows][cols] matrix (pndf_tc_gemm.cuh::tiled_offset): e = ((rt * cols/32 + cb) * T + r) * 32 + c
+        const long long e = i - base;
+        const int cols = rev ? p.n_out[l] : p.k_pad[l], T = rev ? 128 : p.f_tile[l];
+        const int c = (int)(e & 31);
+        const long long q = e >> 5;
+        const int r = (int)(q % T);
+        const long long q2 = q / T;
+        const int cb = (int)(q2 % (cols / 32)), rt = (int)(q2 / (cols / 32));
+        const int row = rt * T + r, col = cb * 32 + c;
+        float w = 0.0f;
+        if (!rev) {      // forward copy: row = output unit n, column = input feature k
+            if (col < p.n_in[l]) w = p.flat[p.w_off[l] + (long long)row * p.n_in[l] + col];
+        } else {         // reverse copy: row = input feature k, column = output unit n
+            if (row < p.n_in[l]) w = p.flat[p.w_off[l] + (long long)col * p.n_in[l] + row];
+        }
+        const float h = tf32_rna(w);
+        p.hi[i] = h;
+        p.lo[i] = tf32_rna(w - h);
+    }
+}
+
+// ---- encoder head of a step: 32-pose tile -> z0 hi / lo
+struct EncParams {
+    const float* pose;       // [B][84]
+    const float* encw;       // 3516 floats or nullptr
+    float* z0_hi;            // [P][z0_ld]
+    float* z0_lo;
+    const float* g0;         // [P][128] (reverse kernel)
+    const float* dist;       // [B]      (reverse kernel: d of this step)
+    float* pose_out;         // [B][84] or nullptr
+    float* grad;             // [B][84] or nullptr
+    float* peer_pose[kMaxPeers];
+    long long B;
+    int z0_ld, normalise, use_enc, enc_act, do_step, renorm, n_peers;
+    float enc_beta;
+};
+constexpr int kEncSmX = 0;                               // [128][32] features (swizzled, as the fused kernel)
+constexpr int kEncSmY = kEncSmX + 128 * 32 * 4;          // [224][32] gradient buffer: rows [0,128) dd/dz0, rows [128,212) qbar
+constexpr int kEncSmW = kEncSmY + 224 * 32 * 4;          // encoder weights
+constexpr int kEncSmXs = kEncSmW + ((kEncFloats * 4 + 127) / 128) * 128;
+constexpr int kEncSmQs = kEncSmXs + kTileM * kXS * 4;
+constexpr int kEncSmNrm = kEncSmQs + kTileM * kXS * 4;
+constexpr int kEncSmTotal = kEncSmNrm + 4 * 32 * 4;
+
+template <bool ESOFT, bool REVERSE>
+__global__ void __launch_bounds__(256) tc_enc_kernel(const EncParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* X = reinterpret_cast<float*>(smem + kEncSmX);
+    float* Y = reinterpret_cast<float*>(smem + kEncSmY);
+    float* encw = reinterpret_cast<float*>(smem + kEncSmW);
+    float* xs = reinterpret_cast<float*>(smem + kEncSmXs);
+    float* qs = reinterpret_cast<float*>(smem + kEncSmQs);
+    float* nrm = reinterpret_cast<float*>(smem + kEncSmNrm);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long pose0 = (long long)blockIdx.x * kTileM;
+    const int nvalid = (int)min((long long)kTileM, p.B - pose0);
+    EncLane enc;
+    enc.l = lane & 7; enc.base = lane & 24; enc.m = warp * 4 + (lane >> 3);
+    const float apar = ESOFT ? p.enc_beta : ((p.enc_act == ACT_RELU) ? 0.0f : 0.01f);
+
+    for (int idx = tid; idx < kTileM * 84; idx += 256) xs[idx] = (idx < nvalid * 84) ? __ldg(p.pose + pose0 * 84 + idx) : 0.0f;
+    if (p.use_enc)
+        for (int i = tid; i < kEncFloats; i += 256) encw[i] = __ldg(p.encw + i);
+    if (REVERSE) {      // dd/dz0 of this tile, pose-major in HBM -> [feature][pose] rows [0, 128) of Y
+        for (int idx = tid; idx < kTileM * 128; idx += 256) {
+            const int m = idx >> 7, f = idx & 127;
+            Y[swz(f, m)] = (m < nvalid) ? __ldg(p.g0 + pndf_tc::tiled_offset(pose0 + m, f, 128)) : 0.0f;
+        }
+    }
+    __syncthreads();
+    // ---- column norms, q = x / n (8 lanes per pose)
+    {
+        const int cpt = enc.l & 3, hf = enc.l >> 2;
+        if (p.normalise) {
+            float sq = 0.0f;
+            for (int j = hf; j < 21; j += 2) {
+                const float x = xs[enc.m * kXS + j * 4 + cpt];
+                sq = fmaf(x, x, sq);
+            }
+            sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+            const float n = fmaxf(sqrtf(sq), 1e-12f);
+            if (hf == 0) nrm[cpt * 32 + enc.m] = n;
+            for (int j = hf; j < 21; j += 2) qs[enc.m * kXS + j * 4 + cpt] = xs[enc.m * kXS + j * 4 + cpt] / n;
+        } else {
+            for (int j = hf; j < 21; j += 2) qs[enc.m * kXS + j * 4 + cpt] = xs[enc.m * kXS + j * 4 + cpt];
+        }
+        __syncwarp();
+        if (p.use_enc) {
+            encoder_forward<ESOFT>(encw, qs, X, nullptr, enc, apar);
+            if (enc.l < 2) X[swz(126 + enc.l, enc.m)] = 0.0f;
+        } else {
+            for (int e = enc.l; e < 128; e += 8) X[swz(e, enc.m)] = (e < 84) ? qs[enc.m * kXS + e] : 0.0f;
+        }
+    }
+    __syncthreads();
+    if (!REVERSE) {
+        // z0 -> pose-major tf32 hi / lo rows of width z0_ld (128 with the encoder, 96 without)
+        const int cols = p.z0_ld;
+        for (int idx = tid; idx < kTileM * (cols / 4); idx += 256) {
+            const int m = idx / (cols / 4), c4 = (idx - m * (cols / 4)) * 4;
+            if (m >= nvalid) continue;
+            float h[4], l[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float z = X[swz(c4 + k, m)];
+                h[k] = tf32_rna(z);
+                l[k] = tf32_rna(z - h[k]);
+            }
+            const size_t off = pndf_tc::tiled_offset(pose0 + m, c4, cols);
+            *reinterpret_cast<float4*>(p.z0_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(p.z0_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+        return;
+    }
+    // ---- reverse: encoder adjoint sweep, Jacobian of the column normalisation, projection step
+    {
+        const int m = enc.m;
+        if (p.use_enc) {
+            encoder_backward<ESOFT>(encw, qs, X, Y, enc, apar);      // qbar -> Y rows [128, 212)
+        } else {
+            for (int e = enc.l; e < 84; e += 8) Y[swz(128 + e, m)] = Y[swz(e, m)];
+            __syncwarp();
+        }
+        const float d = (m < nvalid) ? __ldg(p.dist + pose0 + m) : 0.0f;
+        const int cpt = enc.l & 3, hf = enc.l >> 2;
+        float n = 1.0f, dot = 0.0f;
+        if (p.normalise) {
+            n = nrm[cpt * 32 + m];
+            for (int j = hf; j < 21; j += 2) dot = fmaf(qs[m * kXS + j * 4 + cpt], Y[swz(128 + j * 4 + cpt, m)], dot);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+            if (n <= 1e-12f) dot = 0.0f;
+        }
+        for (int j = hf; j < 21; j += 2) {
+            const int e = j * 4 + cpt;
+            const float x = xs[m * kXS + e];
+            float g = Y[swz(128 + e, m)];
+            if (p.normalise) g = (g - qs[m * kXS + e] * dot) / n;
+            Y[swz(128 + e, m)] = g;
+            if (p.do_step) xs[m * kXS + e] = __fsub_rn(x, __fmul_rn(d, g));
+        }
+        if (p.do_step && p.renorm) {
+            __syncwarp();
+            for (int j = enc.l; j < 21; j += 8) {
+                float sq = 0.0f;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) sq = fmaf(xs[m * kXS + j * 4 + c4], xs[m * kXS + j * 4 + c4], sq);
+                const float inv = 1.0f / sqrtf(sq);
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) xs[m * kXS + j * 4 + c4] *= inv;
+            }
+        }
+    }
+    __syncthreads();
+    if (p.grad != nullptr)
+        for (int idx = tid; idx < nvalid * 84; idx += 256) {
+            const int m = idx / 84, e = idx - m * 84;
+            p.grad[pose0 * 84 + idx] = Y[swz(128 + e, m)];
+        }
+    if (p.pose_out != nullptr)
+        for (int i4 = tid; i4 < nvalid * 21; i4 += 256) {
+            const float4 v = reinterpret_cast<const float4*>(xs)[i4];
+            reinterpret_cast<float4*>(p.pose_out + pose0 * 84)[i4] = v;
+            for (int r = 0; r < p.n_peers; ++r) reinterpret_cast<float4*>(p.peer_pose[r] + pose0 * 84)[i4] = v;
+        }
+}
+
+// ---- layer 6 + output activation + seed of the reverse chain, one thread per pose
+struct HeadParams {
+    const float* z6_hi;      // [P][64]
+    const float* z6_lo;
+    const float* w6;         // 64
+    const float* b6;         // 1
+    const float* g_up;       // [B] or nullptr
+    float* dist;             // [B] or nullptr
+    float* dist_keep;        // [B] internal copy for the reverse kernel (always written)
+    float* peer_dist[kMaxPeers];
+    float* t5_hi;            // [P][64] or nullptr (forward only)
+    float* t5_lo;
+    long long B;
+    int soft, n_peers;
+    float slope, beta;
+};
+__global__ void __launch_bounds__(128) tc_head_kernel(const HeadParams p) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    float z[64];
+    float s = 0.0f;
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) {
+        const size_t off = pndf_tc::tiled_offset(b, 4 * k4, 64);
+        const float4 h = __ldg(reinterpret_cast<const float4*>(p.z6_hi + off));
+        const float4 l = __ldg(reinterpret_cast<const float4*>(p.z6_lo + off));
+        z[4 * k4] = h.x + l.x; z[4 * k4 + 1] = h.y + l.y; z[4 * k4 + 2] = h.z + l.z; z[4 * k4 + 3] = h.w + l.w;
+    }
+    // the fused kernel sums 8 lanes x 8 terms and then a 3-level butterfly; any fixed order is as good against the fp64 oracle
+#pragma unroll
+    for (int k = 0; k < 64; ++k) s = fmaf(__ldg(p.w6 + k), z[k], s);
+    s += __ldg(p.b6);
+    float dv;
+    const float d = act_eval(s, p.soft ? ACT_SOFTPLUS : ACT_RELU, p.beta, dv);
+    p.dist_keep[b] = d;
+    if (p.dist != nullptr) p.dist[b] = d;
+    for (int r = 0; r < p.n_peers; ++r)
+        if (p.peer_dist[r] != nullptr) p.peer_dist[r][b] = d;
+    if (p.t5_hi == nullptr) return;
+    const float gs = (p.g_up != nullptr ? __ldg(p.g_up + b) : 1.0f) * dv;
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) {
+        float h[4], l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float zz = z[4 * k4 + k];
+            const float d5 = p.soft ? -expm1f(-p.beta * zz) : (zz > 0.0f ? 1.0f : p.slope);
+            const float t = gs * __ldg(p.w6 + 4 * k4 + k) * d5;
+            h[k] = tf32_rna(t);
+            l[k] = tf32_rna(t - h[k]);
+        }
+        const size_t off = pndf_tc::tiled_offset(b, 4 * k4, 64);
+        *reinterpret_cast<float4*>(p.t5_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(p.t5_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host side
+struct TcState {
+    pndf_config cfg;
+    int widths[8];                 // in_dim, 256, 512, 1024, 512, 256, 64, 1
+    int kpad[6], ninpad[6];        // K of the forward op l (n_in padded to 32), N of the reverse op l (n_in padded to 128)
+    float *w_hi = nullptr, *w_lo = nullptr;
+    long long f_off[6], r_off[6], w_total = 0;
+    long long w_off_flat[6];
+    // activations for `cap` poses (multiple of 128): forward z_0..z_6 (hi, lo), reverse t_5..t_0 (hi, lo), g0, dist
+    long long cap = 0;
+    float* act = nullptr;
+    long long z_off[7], t_off[6], g0_off = 0, dist_off = 0, act_floats = 0;
+    int num_sms = 148;
+    std::string err;
+};
+
+static int tc_fail(TcState* s, const std::string& m) { s->err = m; return 1; }
+// 0 if the last launch was accepted, else records `what` + the CUDA error string
+static int tc_check(TcState* s, const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return 0;
+    return tc_fail(s, std::string(what) + ": " + cudaGetErrorString(e));
+}
+const char* tc_last_error(TcState* s) { return s ? s->err.c_str() : "null tc state"; }
+
+int tc_create(TcState** out, const pndf_config* cfg) {
+    TcState* s = new TcState();
+    s->cfg = *cfg;
+    const int w[8] = {cfg->in_dim, 256, 512, 1024, 512, 256, 64, 1};
+    long long off = cfg->use_enc ? kEncFloats : 0, tot = 0;
+    for (int l = 0; l < 8; ++l) s->widths[l] = w[l];
+    for (int l = 0; l < 6; ++l) {
+        s->kpad[l] = (w[l] + 31) / 32 * 32;
+        s->ninpad[l] = (w[l] + 127) / 128 * 128;
+        s->w_off_flat[l] = off;
+        off += (long long)w[l + 1] * w[l] + w[l + 1];
+    }
+    for (int l = 0; l < 6; ++l) { s->f_off[l] = tot; tot += (long long)w[l + 1] * s->kpad[l]; }
+    for (int l = 0; l < 6; ++l) { s->r_off[l] = tot; tot += (long long)s->ninpad[l] * w[l + 1]; }
+    s->w_total = tot;
+    cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    if (cudaMalloc(&s->w_hi, tot * sizeof(float)) != cudaSuccess || cudaMalloc(&s->w_lo, tot * sizeof(float)) != cudaSuccess) {
+        tc_destroy(s);
+        return 1;
+    }
+    if (!pndf_tc::encode_fn()) {
+        tc_destroy(s);
+        return 1;
+    }
+    *out = s;
+    return 0;
+}
+
+void tc_destroy(TcState* s) {
+    if (!s) return;
+    cudaFree(s->w_hi);
+    cudaFree(s->w_lo);
+    cudaFree(s->act);
+    delete s;
+}
+
+int tc_set_weights(TcState* s, const float* flat_dev, cudaStream_t st) {
+    SplitParams p{};
+    p.flat = flat_dev; p.hi = s->w_hi; p.lo = s->w_lo; p.total = s->w_total;
+    for (int l = 0; l < 6; ++l) {
+        p.w_off[l] = s->w_off_flat[l]; p.f_off[l] = s->f_off[l]; p.r_off[l] = s->r_off[l];
+        p.n_in[l] = s->widths[l]; p.n_out[l] = s->widths[l + 1]; p.k_pad[l] = s->kpad[l]; p.n_in_pad[l] = s->ninpad[l];
+        p.f_tile[l] = (s->widths[l + 1] % 128 == 0) ? 128 : 64;
+    }
+    tc_split_weights_kernel<<<148 * 8, 256, 0, st>>>(p);
+    return tc_check(s, "tc_split_weights_kernel launch");
+}
+
+static int ensure_act(TcState* s, long long B) {
+    const long long P = (B + 127) / 128 * 128;
+    if (P <= s->cap) return 0;
+    cudaFree(s->act);
+    s->act = nullptr;
+    long long off = 0;
+    const int zw[7] = {s->kpad[0], 256, 512, 1024, 512, 256, 64};
+    for (int l = 0; l < 7; ++l) { s->z_off[l] = off; off += 2 * P * zw[l]; }
+    const int tw[6] = {256, 512, 1024, 512, 256, 64};      // t_l has the width of layer l's output
+    for (int l = 0; l < 6; ++l) { s->t_off[l] = off; off += 2 * P * tw[l]; }
+    s->g0_off = off; off += P * 128;
+    s->dist_off = off; off += P;
+    if (cudaMalloc(&s->act, off * sizeof(float)) != cudaSuccess) return tc_fail(s, "tensor-core path: cannot allocate the activation buffers");
+    if (cudaMemset(s->act, 0, off * sizeof(float)) != cudaSuccess) return tc_fail(s, "cudaMemset failed");
+    s->cap = P;
+    s->act_floats = off;
+    return 0;
+}
+
+template <int NT, class Epi>
+static int launch_gemm(TcState* s, const float* a_hi, const float* a_lo, long long P, int K, const float* b_hi, const float* b_lo, int N,
+                       const Epi& epi, cudaStream_t st) {
+    using namespace pndf_tc;
+    GemmMaps maps;
+    if (!make_map(&maps.a_hi, a_hi, P, K, pndf_tc::kTM) || !make_map(&maps.a_lo, a_lo, P, K, pndf_tc::kTM) || !make_map(&maps.b_hi, b_hi, N, K, NT) ||
+        !make_map(&maps.b_lo, b_lo, N, K, NT))
+        return tc_fail(s, "cuTensorMapEncodeTiled failed");
+    auto kern = tc_gemm_kernel<NT, Epi>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pndf_tc::smem_bytes<NT>()) != cudaSuccess)
+        return tc_fail(s, "cudaFuncSetAttribute failed");
+    // (pndf::kThreads is the fused kernel's 256; this kernel is compiled for pndf_tc::kThreads = 192)
+    const int m_tiles = (int)(P / pndf_tc::kTM), n_tiles = N / NT;
+    const int grid = std::min(m_tiles * n_tiles, s->num_sms);
+    kern<<<grid, pndf_tc::kThreads, pndf_tc::smem_bytes<NT>(), st>>>(maps, K, m_tiles, n_tiles, epi);
+    return tc_check(s, "tc_gemm_kernel launch");
+}
+
+int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
+    if (ensure_act(s, a.B)) return 1;
+    const long long P = (a.B + 127) / 128 * 128;
+    const pndf_config& cfg = s->cfg;
+    const bool dsoft = cfg.df_act == PNDF_ACT_SOFTPLUS, esoft = cfg.enc_act == PNDF_ACT_SOFTPLUS;
+    const float dpar = dsoft ? cfg.df_beta : (cfg.df_act == PNDF_ACT_RELU ? 0.0f : 0.01f);
+    const int zw[7] = {s->kpad[0], 256, 512, 1024, 512, 256, 64};
+    auto zhi = [&](int l) { return s->act + s->z_off[l]; };
+    auto zlo = [&](int l) { return s->act + s->z_off[l] + P * zw[l]; };
+    auto thi = [&](int l) { return s->act + s->t_off[l]; };
+    auto tlo = [&](int l) { return s->act + s->t_off[l] + P * s->widths[l + 1]; };
+    float* g0 = s->act + s->g0_off;
+    float* dkeep = s->act + s->dist_off;
+    cudaFuncSetAttribute(tc_enc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmTotal);
+    cudaFuncSetAttribute(tc_enc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmTotal);
+    cudaFuncSetAttribute(tc_enc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmTotal);
+    cudaFuncSetAttribute(tc_enc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmTotal);
+    const unsigned tiles32 = (unsigned)((a.B + kTileM - 1) / kTileM);
+    const float* pose_cur = a.pose_in;
+    for (int step = 0; step < a.steps; ++step) {
+        const bool last = (step == a.steps - 1);
+        EncParams ep{};
+        ep.pose = pose_cur; ep.encw = a.encw; ep.z0_hi = zhi(0); ep.z0_lo = zlo(0); ep.B = a.B; ep.z0_ld = zw[0];
+        ep.normalise = a.normalise; ep.use_enc = cfg.use_enc; ep.enc_act = cfg.enc_act; ep.enc_beta = cfg.enc_beta;
+        if (esoft) tc_enc_kernel<true, false><<<tiles32, 256, kEncSmTotal, st>>>(ep);
+        else tc_enc_kernel<false, false><<<tiles32, 256, kEncSmTotal, st>>>(ep);
+        if (tc_check(s, "tc_enc_kernel (forward) launch")) return 1;
+        // ---- forward chain
+        for (int l = 0; l < 6; ++l) {
+            FwdEpi fe{a.bias[l], zhi(l + 1), zlo(l + 1), zw[l + 1], dsoft ? 1 : 0, dpar};
+            const float* bh = s->w_hi + s->f_off[l];
+            const float* bl = s->w_lo + s->f_off[l];
+            const int N = s->widths[l + 1];
+            const int rc = (N % 128 == 0) ? launch_gemm<128>(s, zhi(l), zlo(l), P, s->kpad[l], bh, bl, N, fe, st)
+                                          : launch_gemm<64>(s, zhi(l), zlo(l), P, s->kpad[l], bh, bl, N, fe, st);
+            if (rc) return 1;
+        }
+        HeadParams hp{};
+        hp.z6_hi = zhi(6); hp.z6_lo = zlo(6); hp.w6 = a.w6; hp.b6 = a.bias[6]; hp.g_up = a.g_up; hp.B = a.B;
+        hp.dist = last ? a.dist : nullptr; hp.dist_keep = dkeep; hp.soft = dsoft ? 1 : 0; hp.slope = dsoft ? 0.0f : dpar; hp.beta = cfg.df_beta;
+        if (last) { hp.n_peers = a.n_peers; for (int r = 0; r < a.n_peers; ++r) hp.peer_dist[r] = a.peer_dist[r]; }
+        if (a.want_grad) { hp.t5_hi = thi(5); hp.t5_lo = tlo(5); }
+        tc_head_kernel<<<(unsigned)((a.B + 127) / 128), 128, 0, st>>>(hp);
+        if (tc_check(s, "tc_head_kernel launch")) return 1;
+        if (launches) *launches += 8;
+        if (!a.want_grad) break;
+        // ---- reverse chain: op l maps t_l (width n_out[l]) through W_l to the input side (width n_in[l])
+        for (int l = 5; l >= 0; --l) {
+            const float* bh = s->w_hi + s->r_off[l];
+            const float* bl = s->w_lo + s->r_off[l];
+            const int K = s->widths[l + 1], N = s->ninpad[l];
+            int rc;
+            if (l > 0) {
+                BwdEpi be{zhi(l), zlo(l), thi(l - 1), tlo(l - 1), zw[l], dsoft ? 1 : 0, dpar};
+                rc = launch_gemm<128>(s, thi(l), tlo(l), P, K, bh, bl, N, be, st);
+            } else {
+                G0Epi ge{g0, 128};
+                rc = launch_gemm<128>(s, thi(0), tlo(0), P, K, bh, bl, N, ge, st);
+            }
+            if (rc) return 1;
+        }
+        EncParams rp = ep;
+        rp.g0 = g0; rp.dist = dkeep; rp.do_step = a.do_step; rp.renorm = a.renorm;
+        rp.grad = last ? a.grad : nullptr;
+        rp.pose_out = a.do_step ? a.pose_out : nullptr;
+        if (last && a.do_step) { rp.n_peers = a.n_peers; for (int r = 0; r < a.n_peers; ++r) rp.peer_pose[r] = a.peer_pose[r]; }
+        if (esoft) tc_enc_kernel<true, true><<<tiles32, 256, kEncSmTotal, st>>>(rp);
+        else tc_enc_kernel<false, true><<<tiles32, 256, kEncSmTotal, st>>>(rp);
+        if (tc_check(s, "tc_enc_kernel (reverse) launch")) return 1;
+        if (launches) *launches += 7;
+        pose_cur = a.pose_out;       // the next step starts from the projected poses
+    }
+    return 0;
+}
+
+}  // namespace pndf

@@ -1,0 +1,38 @@
+// pndf_tc.h -- host interface of the tensor-core DFNet path (pndf_tc.cu), used by pndf_capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/pndf.h"
+
+namespace pndf {
+
+struct TcState;
+
+struct TcArgs {
+    const float* pose_in = nullptr;   // [B][84] quaternion poses
+    float* pose_out = nullptr;        // [B][84] (projection) or nullptr
+    float* dist = nullptr;            // [B] or nullptr
+    float* grad = nullptr;            // [B][84] or nullptr
+    const float* g_up = nullptr;      // [B] or nullptr
+    long long B = 0;
+    int steps = 1, do_step = 0, renorm = 0, normalise = 1, want_grad = 1;
+    const float* encw = nullptr;      // encoder parameters (reference order) or nullptr
+    const float* bias[7] = {};        // dfnet.lin{l}.bias
+    const float* w6 = nullptr;        // dfnet.lin6.weight
+    float* peer_pose[7] = {};         // fused gather (see KParams)
+    float* peer_dist[7] = {};
+    int n_peers = 0;
+};
+
+int tc_create(TcState** out, const pndf_config* cfg);
+void tc_destroy(TcState* s);
+// split the flat fp32 parameter vector (reference order, device pointer) into the tf32 hi / lo weight copies; stream-ordered
+int tc_set_weights(TcState* s, const float* flat_dev, cudaStream_t st);
+// forward (want_grad = 0), forward + gradient, or `steps` projection steps; *launches is increased by the kernels launched
+int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches);
+const char* tc_last_error(TcState* s);
+
+}  // namespace pndf

@@ -17,7 +17,7 @@
 //   warps 2-5   drain: tcgen05.ld both accumulators of the finished pair, add into 128 running fp32 sums per thread (thread = one
 //               output row = one TMEM lane), hand the pair back (`acc_empty`) so that the next-but-one chunk can overwrite it --
 //               the drain of chunk c runs under the MMAs of chunk c+1 (two pairs = 4 x NT TMEM columns); finally the epilogue
-//               functor turns the 128-float row segment into whatever the layer needs.
+//               functor turns the 128-float row segment into whatever the layer needs (stored coalesced through shared memory).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -55,6 +55,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
                      smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
 // K-major SWIZZLE_128B shared-memory matrix descriptor (8-row x 128-byte atoms, 1024 bytes apart)
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -87,19 +90,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr));
 }
 
+// TILED matrix layout of every GEMM operand / result: a [R][C] matrix (C a multiple of 32) is stored as
+// [R / T][C / 32][T][32] floats -- T-row tile, 32-column (128-byte) K block -- so that a TMA box of T rows x 32 columns is one
+// contiguous T * 128-byte block and a warp's 32 rows x 32 columns of an output tile are 4 KB contiguous.  T = 128 for
+// activations, the N tile (128 or 64) for weights.
+__host__ __device__ __forceinline__ size_t tiled_offset(long long r, int c, int C, int T = kTM) {
+    return ((size_t)((r / T) * (C / 32) + c / 32) * T + (size_t)(r % T)) * 32 + (size_t)(c % 32);
+}
+
 template <int NT>
 __host__ __device__ constexpr int stage_bytes() { return 2 * kTM * 128 + 2 * NT * 128; }
+constexpr int kStageRow = 33;            // padded row of the per-warp output staging tile (32 x 32 floats)
 template <int NT>
-__host__ __device__ constexpr int smem_bytes() { return kStages * stage_bytes<NT>() + 1024 + 256; }
+__host__ __device__ constexpr int smem_bytes() { return kStages * stage_bytes<NT>() + 1024 + 256 + 4 * 32 * kStageRow * 4; }
 
 struct GemmMaps {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-// Epilogue functor interface: void operator()(int row /*global*/, int col0 /*global, multiple of 32*/, float (&v)[32]) -- called by
-// the thread that owns `row` for every 32-column group of its tile.
+// Epilogue functor interface:
+//   static constexpr int kOutputs            1 or 2 output arrays
+//   void operator()(int row, int col0, const float (&v)[32], float (&o0)[32], float (&o1)[32]) const
+//                                            called by the thread that owns `row` for every 32-column group of its tile
+//   float* out(int which) const, int ld()    the output arrays (row-major, row length ld)
+// The kernel stores the outputs itself, coalesced through a per-warp shared-memory staging tile.
+//
+// Persistent: gridDim.x CTAs walk the (m_tile, n_tile) list (n fastest: the CTAs that share an A tile run together).  The running
+// sums live in the drain warps' registers, so the TMEM accumulator pairs are free as soon as a tile's last chunk is drained: the
+// MMA warp starts the next tile while the drain warps are still busy with the previous tile's epilogue (activation, hi / lo split,
+// stores).
 template <int NT, class Epilogue>
-__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmMaps maps, int K, Epilogue epi) {
+__global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmMaps maps, int K, int m_tiles, int n_tiles,
+                                                              Epilogue epi) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes<NT>());
@@ -108,9 +130,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     uint64_t* acc_full = bars + 2 * kStages; // [2]
     uint64_t* acc_empty = acc_full + 2;      // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* staging = reinterpret_cast<float*>(smem + kStages * stage_bytes<NT>() + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * NT, m0 = blockIdx.y * kTM;
     const int nks = K / kKB;
+    constexpr int kStagesPerChunk = kChunkK / kKB;
+    const int nchunks = (nks + kStagesPerChunk - 1) / kStagesPerChunk;
+    const int ntiles = m_tiles * n_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -129,15 +154,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            for (int ks = 0; ks < nks; ++ks) {
-                const int s = ks % kStages;
-                mbar_wait(&empty[s], ((ks / kStages) & 1) ^ 1);      // fresh barrier: parity 1 passes
-                uint8_t* st = smem + s * stage_bytes<NT>();
-                mbar_expect_tx(&full[s], stage_bytes<NT>());
-                tma_load_2d(st, &maps.a_hi, ks * kKB, m0, &full[s]);
-                tma_load_2d(st + kTM * 128, &maps.a_lo, ks * kKB, m0, &full[s]);
-                tma_load_2d(st + 2 * kTM * 128, &maps.b_hi, ks * kKB, n0, &full[s]);
-                tma_load_2d(st + 2 * kTM * 128 + NT * 128, &maps.b_lo, ks * kKB, n0, &full[s]);
+            uint32_t it = 0;      // running stage counter over all tiles of this CTA
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * NT;
+                for (int ks = 0; ks < nks; ++ks, ++it) {
+                    const uint32_t s = it % kStages;
+                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);      // fresh barrier: parity 1 passes
+                    uint8_t* st = smem + s * stage_bytes<NT>();
+                    mbar_expect_tx(&full[s], stage_bytes<NT>());
+                    // operands live in TILED layout: [row tile][K block][rows of the tile][32 floats] -- every TMA box (rows x 128 bytes) is
+                    // one contiguous 16 KB (8 KB) block of memory instead of 128 row segments 2-4 KB apart
+                    const int ra = ((tile / n_tiles) * nks + ks) * kTM, rb = ((tile % n_tiles) * nks + ks) * NT;
+                    tma_load_2d(st, &maps.a_hi, 0, ra, &full[s]);
+                    tma_load_2d(st + kTM * 128, &maps.a_lo, 0, ra, &full[s]);
+                    tma_load_2d(st + 2 * kTM * 128, &maps.b_hi, 0, rb, &full[s]);
+                    tma_load_2d(st + 2 * kTM * 128 + NT * 128, &maps.b_lo, 0, rb, &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -145,59 +177,85 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         if (lane == 0) {
             // D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
-            constexpr int kStagesPerChunk = kChunkK / kKB;
-            for (int ks = 0; ks < nks; ++ks) {
-                const int s = ks % kStages, c = ks / kStagesPerChunk, p = c & 1;
-                const bool chunk_start = (ks % kStagesPerChunk) == 0;
-                if (chunk_start) mbar_wait(&acc_empty[p], ((c >> 1) & 1) ^ 1);      // the drain of chunk c-2 has emptied pair p
-                mbar_wait(&full[s], (ks / kStages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t st = smem_u32(smem + s * stage_bytes<NT>());
-                const uint32_t a_hi = st, a_lo = st + kTM * 128, b_hi = st + 2 * kTM * 128, b_lo = b_hi + NT * 128;
-                const uint32_t acc_hh = tmem + (uint32_t)(p * 2 * NT), acc_x = acc_hh + NT;
+            uint32_t it = 0, cc = 0;      // running stage / chunk counters
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int ks = 0; ks < nks; ++ks, ++it) {
+                    const uint32_t s = it % kStages, p = cc & 1;
+                    const bool chunk_start = (ks % kStagesPerChunk) == 0;
+                    if (chunk_start) mbar_wait(&acc_empty[p], ((cc >> 1) & 1) ^ 1);      // the drain of chunk cc-2 has emptied pair p
+                    mbar_wait(&full[s], (it / kStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;");
+                    const uint32_t st = smem_u32(smem + s * stage_bytes<NT>());
+                    const uint32_t a_hi = st, a_lo = st + kTM * 128, b_hi = st + 2 * kTM * 128, b_lo = b_hi + NT * 128;
+                    const uint32_t acc_hh = tmem + (uint32_t)(p * 2 * NT), acc_x = acc_hh + NT;
 #pragma unroll
-                for (int k = 0; k < kKB / 8; ++k) {
-                    const uint32_t first = (chunk_start && k == 0) ? 0u : 1u;
-                    mma_tf32(acc_hh, make_desc(a_hi + k * 32), make_desc(b_hi + k * 32), idesc, first);
-                    mma_tf32(acc_x, make_desc(a_lo + k * 32), make_desc(b_hi + k * 32), idesc, first);
-                    mma_tf32(acc_x, make_desc(a_hi + k * 32), make_desc(b_lo + k * 32), idesc, 1u);
+                    for (int k = 0; k < kKB / 8; ++k) {
+                        const uint32_t first = (chunk_start && k == 0) ? 0u : 1u;
+                        mma_tf32(acc_hh, make_desc(a_hi + k * 32), make_desc(b_hi + k * 32), idesc, first);
+                        mma_tf32(acc_x, make_desc(a_lo + k * 32), make_desc(b_hi + k * 32), idesc, first);
+                        mma_tf32(acc_x, make_desc(a_hi + k * 32), make_desc(b_lo + k * 32), idesc, 1u);
+                    }
+                    mma_commit(&empty[s]);                                               // stage s may be refilled once these MMAs retire
+                    if ((ks % kStagesPerChunk) == kStagesPerChunk - 1 || ks == nks - 1) {
+                        mma_commit(&acc_full[p]);
+                        ++cc;
+                    }
                 }
-                mma_commit(&empty[s]);                                               // stage s may be refilled once these MMAs retire
-                if ((ks % kStagesPerChunk) == kStagesPerChunk - 1 || ks == nks - 1) mma_commit(&acc_full[p]);
             }
         }
     } else {
         // ------------------------------------------------------------------ drain + epilogue: thread = output row
         const int quarter = warp & 3;                       // TMEM lanes [32 q, 32 q + 32) are this warp's
-        const int row = m0 + quarter * 32 + lane;
-        float run[NT];
+        float* stg = staging + (warp - 2) * (32 * kStageRow);
+        uint32_t cc = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * NT;
+            const int row = m0 + quarter * 32 + lane;
+            float run[NT];
 #pragma unroll
-        for (int j = 0; j < NT; ++j) run[j] = 0.0f;
-        const int nchunks = (K + kChunkK - 1) / kChunkK;
-        for (int c = 0; c < nchunks; ++c) {
-            const int p = c & 1;
-            mbar_wait(&acc_full[p], (c >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;");
-            const uint32_t base = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p * 2 * NT);
+            for (int j = 0; j < NT; ++j) run[j] = 0.0f;
+            for (int c = 0; c < nchunks; ++c, ++cc) {
+                const uint32_t p = cc & 1;
+                mbar_wait(&acc_full[p], (cc >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t base = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p * 2 * NT);
+#pragma unroll
+                for (int g = 0; g < NT / 32; ++g) {
+                    uint32_t hh[32], xx[32];
+                    tmem_ld32(base + g * 32, hh);
+                    tmem_ld32(base + NT + g * 32, xx);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) run[g * 32 + j] += __uint_as_float(hh[j]) + __uint_as_float(xx[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[p]);
+            }
+            // epilogue of this tile (the MMA warp is already on the next one)
 #pragma unroll
             for (int g = 0; g < NT / 32; ++g) {
-                uint32_t hh[32], xx[32];
-                tmem_ld32(base + g * 32, hh);
-                tmem_ld32(base + NT + g * 32, xx);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float v[32], o0[32], o1[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) run[g * 32 + j] += __uint_as_float(hh[j]) + __uint_as_float(xx[j]);
+                for (int j = 0; j < 32; ++j) v[j] = run[g * 32 + j];
+                epi(row, n0 + g * 32, v, o0, o1);
+#pragma unroll
+                for (int w = 0; w < Epilogue::kOutputs; ++w) {
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) stg[lane * kStageRow + j] = (w == 0) ? o0[j] : o1[j];
+                    __syncwarp();
+                    // tiled output (the next GEMM's A operand): this warp's 32 rows x 32 columns are ONE contiguous 4 KB block;
+                    // lane -> (row i*4 + lane/8, 16-byte chunk lane%8): 512 contiguous bytes per store instruction
+                    float* out = epi.out(w) + tiled_offset(m0 + quarter * 32, n0 + g * 32, epi.ld());
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + (lane >> 3), c4 = (lane & 7) * 4;
+                        const float* sp = stg + r * kStageRow + c4;
+                        *reinterpret_cast<float4*>(out + r * 32 + c4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                    }
+                }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[p]);
-        }
-#pragma unroll
-        for (int g = 0; g < NT / 32; ++g) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = run[g * 32 + j];
-            epi(row, n0 + g * 32, v);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -221,12 +279,13 @@ inline EncodeTiledFn encode_fn() {
     }
     return fn;
 }
-// fp32 row-major matrix [rows][ld] (K contiguous, ld >= K, ld * 4 a multiple of 16): boxes of `box_rows` rows x 32 columns, 128B swizzle
-inline bool make_map(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows) {
+// tiled fp32 matrix [rows][K] (see tiled_offset, tile = box_rows): as a 2-D array of rows * K / 32 rows of 32 floats; a box =
+// box_rows consecutive rows = one contiguous block; 128B swizzle on the way into shared memory
+inline bool make_map(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
-    const cuuint64_t dims[2] = {K, rows};
-    const cuuint64_t strides[1] = {ld * sizeof(float)};
+    const cuuint64_t dims[2] = {32, rows * (K / 32)};
+    const cuuint64_t strides[1] = {32 * sizeof(float)};
     const cuuint32_t box[2] = {(cuuint32_t)kKB, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

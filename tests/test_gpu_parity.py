@@ -15,10 +15,11 @@ pytestmark = pytest.mark.gpu
 CASES = golden_case_names()
 
 
-@pytest.fixture(autouse=True, params=["auto", "32", "8"])
+@pytest.fixture(autouse=True, params=["auto", "32", "8", "128"])
 def tile_size(request, monkeypatch):
-    """every test of this file runs with the library's own choice of tile (32-pose tiles, or the 8-pose small-tile kernels for
-    batches that cannot fill the SMs) and with either kernel family forced (PNDF_TILE, csrc/pndf_capi.cu::use_small_tile)"""
+    """every test of this file runs with the library's own choice of path (tensor-core DFNet for large batches, 32-pose FFMA tiles,
+    8-pose small-tile kernels for batches that cannot fill the SMs) and with each of them forced (PNDF_TILE = 128 / 32 / 8,
+    csrc/pndf_capi.cu::use_tc / use_small_tile)"""
     if request.param == "auto":
         monkeypatch.delenv("PNDF_TILE", raising=False)
     else:
