@@ -270,7 +270,7 @@ int pndf_knn_exact(int device, const float* query_dev, int64_t Q, const float* d
  *   pndf_launch_count: number of kernel launches this handle has enqueued so far. */
 /* Tile size / arithmetic path of the forward / forward+reverse launches.  By default every launch picks it from ITS batch size:
  * the tensor-core path ("tile 128": DFNet GEMMs as 3xTF32 tcgen05 kernels on 128-pose tiles, pndf_tc.cu) for plain quaternion
- * batches of >= 16 384 poses, else the fused FFMA kernel with 32-pose tiles, or its 8-pose small-tile variant while the 32-pose
+ * batches of >= 6 144 poses, else the fused FFMA kernel with 32-pose tiles, or its 8-pose small-tile variant while the 32-pose
  * tiling cannot give every SM a tile (B <= ~2 400; 2.4x lower latency at the reference's real call sites, B = 10 in
  * experiments/sample_poses.py:96).  The paths differ in fp32 summation order / split arithmetic (same parity bars), so a caller that splits ONE batch over several launches or GPUs and wants bits identical to the unsplit
  * run pins the tile the whole batch would get: tile = pndf_tile_for_batch(h, B_total), pndf_set_tile_policy(h, tile), launches,

@@ -44,7 +44,8 @@ int fail(const std::string& msg) {
 
 const int kAmassDims[6] = {256, 512, 1024, 512, 256, 64};
 const double kSmallTileCost = 0.40;      // time of an 8-pose tile relative to a 32-pose tile (measured)
-const long long kTcMinBatch = 16384;     // from this batch size on the DFNet GEMMs run on the tensor cores (pndf_tc.cu)
+const long long kTcChunk = 131072;       // poses per pass of the tensor-core path (5.7 GB of activations)
+const long long kTcMinBatch = 6144;      // from this batch size on the DFNet GEMMs run on the tensor cores (pndf_tc.cu; measured crossover ~4 096)
 
 }  // namespace
 
@@ -78,6 +79,7 @@ struct pndf_handle {
     int64_t launches = 0;
     // host pipeline (pndf_project_host)
     cudaStream_t hs[2] = {nullptr, nullptr};
+    cudaEvent_t hs_ev = nullptr;
     float* d_chunk[2] = {nullptr, nullptr};
     float* d_chunk_dist[2] = {nullptr, nullptr};
     int64_t chunk_poses = 0;
@@ -377,7 +379,22 @@ int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st, int slot = 0) 
         for (int l = 0; l < 7; ++l) a.bias[l] = p.bias[l];
         for (int r = 0; r < p.n_peers; ++r) { a.peer_pose[r] = p.peer_pose[r]; a.peer_dist[r] = p.peer_dist[r]; }
         if (!h->in_capture && order_after_weights(h, st)) return 1;
-        if (tc_run(h->tc, a, st, &h->launches)) return fail(std::string("tensor-core path: ") + tc_last_error(h->tc));
+        // the activations of the whole DFNet chain live in HBM between the layer kernels (43.5 KB per pose): bound them by walking
+        // very large batches in chunks of kTcChunk poses (every pose is independent; all steps of a chunk run before the next chunk)
+        for (long long off = 0; off < p.B; off += kTcChunk) {
+            TcArgs c = a;
+            c.B = std::min<long long>(kTcChunk, p.B - off);
+            c.pose_in = a.pose_in + off * 84;
+            if (a.pose_out) c.pose_out = a.pose_out + off * 84;
+            if (a.dist) c.dist = a.dist + off;
+            if (a.grad) c.grad = a.grad + off * 84;
+            if (a.g_up) c.g_up = a.g_up + off;
+            for (int r = 0; r < a.n_peers; ++r) {
+                c.peer_pose[r] = a.peer_pose[r] + off * 84;
+                if (a.peer_dist[r]) c.peer_dist[r] = a.peer_dist[r] + off;
+            }
+            if (tc_run(h->tc, c, st, &h->launches)) return fail(std::string("tensor-core path: ") + tc_last_error(h->tc));
+        }
         if (h->in_capture) return 0;
         CUDA_OK(cudaEventRecord(h->use_event, st));
         h->use_stream = st;
@@ -470,6 +487,7 @@ int pndf_destroy(pndf_handle* h) {
     cudaFree(h->d_loss_totals);
     for (int i = 0; i < 2; ++i) {
         if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+        if (i == 0 && h->hs_ev) cudaEventDestroy(h->hs_ev);
         cudaFree(h->d_chunk[i]);
         cudaFree(h->d_chunk_dist[i]);
     }
@@ -628,6 +646,7 @@ int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out
             CUDA_OK(cudaMalloc(&h->d_chunk_dist[i], chunk * sizeof(float)));
         }
         h->chunk_poses = chunk;
+        if (cudaEventCreateWithFlags(&h->hs_ev, cudaEventDisableTiming) != cudaSuccess) h->hs_ev = nullptr;
     }
     if (ensure_slot(h, 1) || ensure_slot(h, 2)) return 1;   // the two streams overlap: each needs its own per-CTA scratch
     // one tile size for all chunks, the one the whole batch would get: the result equals pndf_project on the same batch bit for bit
@@ -642,7 +661,12 @@ int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out
         KParams p{};
         p.pose_in = h->d_chunk[which]; p.pose_out = h->d_chunk[which]; p.dist = h->d_chunk_dist[which]; p.B = nb;
         p.steps = steps; p.do_step = 1; p.renorm = renorm; p.normalise = 1; p.input_kind = IN_QUAT;
+        // the tensor-core path keeps its activations in ONE set of buffers per handle: its launches of consecutive chunks must not
+        // overlap (the copies of the two streams still do)
+        const bool serial = (h->tile_policy == 128) && h->hs_ev != nullptr;
+        if (serial && off > 0) CUDA_OK(cudaStreamWaitEvent(st, h->hs_ev, 0));
         if (launch(h, p, 1, st, 1 + which)) return 1;
+        if (serial) CUDA_OK(cudaEventRecord(h->hs_ev, st));
         CUDA_OK(cudaMemcpyAsync(pose_out_host + off * 84, h->d_chunk[which], nb * 84 * sizeof(float), cudaMemcpyDeviceToHost, st));
         if (dist_host) CUDA_OK(cudaMemcpyAsync(dist_host + off, h->d_chunk_dist[which], nb * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
