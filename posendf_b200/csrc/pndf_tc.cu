@@ -458,7 +458,7 @@ static int launch_gemm(TcState* s, const float* a_hi, const float* a_lo, long lo
     auto kern = tc_gemm_kernel<NT, Epi>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pndf_tc::smem_bytes<NT>()) != cudaSuccess)
         return tc_fail(s, "cudaFuncSetAttribute failed");
-    // (pndf::kThreads is the fused kernel's 256; this kernel is compiled for pndf_tc::kThreads = 192)
+    // (pndf::kThreads is the fused kernel's 256; this kernel is compiled for pndf_tc::kThreads = 320)
     const int m_tiles = (int)(P / pndf_tc::kTM), n_tiles = N / NT;
     const int grid = std::min(m_tiles * n_tiles, s->num_sms);
     kern<<<grid, pndf_tc::kThreads, pndf_tc::smem_bytes<NT>(), st>>>(maps, K, m_tiles, n_tiles, epi);

@@ -9,13 +9,13 @@
 // terms in SEPARATE TMEM accumulators, a fresh accumulator pair per 128-deep K chunk; pairs are added in fp32 (round to nearest)
 // on the CUDA cores -- the tensor core's accumulator truncates, so the long sum must not live in it.
 //
-// One CTA = one 128 x NT output tile (NT = 128 or 64), 192 threads, warp-specialised:
+// Persistent CTAs walk 128 x NT output tiles (NT = 128 or 64); 320 threads, warp-specialised:
 //   warp 0      TMA producer: per 32-deep K stage four tile loads (A_hi, A_lo 128 x 32, B_hi, B_lo NT x 32, SWIZZLE_128B) on a
 //               `full` mbarrier; 3 stages in flight
 //   warp 1      MMA issuer (one lane): 12 MMAs per stage; tcgen05.commit releases the stage (`empty`) and, at the end of a K chunk,
 //               publishes the accumulator pair (`acc_full`)
-//   warps 2-5   drain: tcgen05.ld both accumulators of the finished pair, add into 128 running fp32 sums per thread (thread = one
-//               output row = one TMEM lane), hand the pair back (`acc_empty`) so that the next-but-one chunk can overwrite it --
+//   warps 2-9   drain, two warps per TMEM lane quarter: tcgen05.ld both accumulators of the finished pair, add into NT / 2 running
+//               fp32 sums per thread (thread = one output row x half of the columns), hand the pair back (`acc_empty`) so that the next-but-one chunk can overwrite it --
 //               the drain of chunk c runs under the MMAs of chunk c+1 (two pairs = 4 x NT TMEM columns); finally the epilogue
 //               functor turns the 128-float row segment into whatever the layer needs (stored coalesced through shared memory).
 #pragma once
@@ -29,7 +29,8 @@ constexpr int kTM = 128;                 // rows (poses) per tile = TMEM lanes
 constexpr int kKB = 32;                  // K per stage = one 128-byte swizzle row of tf32
 constexpr int kStages = 3;
 constexpr int kChunkK = 128;             // K depth per accumulator pair
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;            // warp 0 TMA, warp 1 MMA, warps 2-9 drain / epilogue
+constexpr int kDrainWarps = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -102,7 +103,7 @@ template <int NT>
 __host__ __device__ constexpr int stage_bytes() { return 2 * kTM * 128 + 2 * NT * 128; }
 constexpr int kStageRow = 33;            // padded row of the per-warp output staging tile (32 x 32 floats)
 template <int NT>
-__host__ __device__ constexpr int smem_bytes() { return kStages * stage_bytes<NT>() + 1024 + 256 + 4 * 32 * kStageRow * 4; }
+__host__ __device__ constexpr int smem_bytes() { return kStages * stage_bytes<NT>() + 1024 + 256 + kDrainWarps * 32 * kStageRow * 4; }
 
 struct GemmMaps {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int p = 0; p < 2; ++p) { mbar_init(&acc_full[p], 1); mbar_init(&acc_empty[p], 4); }
+        for (int p = 0; p < 2; ++p) { mbar_init(&acc_full[p], 1); mbar_init(&acc_empty[p], kDrainWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -204,23 +205,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             }
         }
     } else {
-        // ------------------------------------------------------------------ drain + epilogue: thread = output row
+        // ------------------------------------------------------------------ drain + epilogue: thread = output row x half of the columns
+        // (two warps per TMEM lane quarter, each owning NT / 2 columns: with four fat drain warps the accumulator pairs -- and with
+        // them the MMA warp -- waited for the drain: 3.46 -> 2.86 ms per 65 536-pose step; sixteen thin ones with direct stores
+        // were slower again, 3.15 ms)
         const int quarter = warp & 3;                       // TMEM lanes [32 q, 32 q + 32) are this warp's
+        const int half = (warp - 2) >> 2;                   // columns [half * NT / 2, (half + 1) * NT / 2)
+        constexpr int NH = NT / 2;
         float* stg = staging + (warp - 2) * (32 * kStageRow);
         uint32_t cc = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * NT;
             const int row = m0 + quarter * 32 + lane;
-            float run[NT];
+            float run[NH];
 #pragma unroll
-            for (int j = 0; j < NT; ++j) run[j] = 0.0f;
+            for (int j = 0; j < NH; ++j) run[j] = 0.0f;
             for (int c = 0; c < nchunks; ++c, ++cc) {
                 const uint32_t p = cc & 1;
                 mbar_wait(&acc_full[p], (cc >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t base = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p * 2 * NT);
+                const uint32_t base = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p * 2 * NT + half * NH);
 #pragma unroll
-                for (int g = 0; g < NT / 32; ++g) {
+                for (int g = 0; g < NH / 32; ++g) {
                     uint32_t hh[32], xx[32];
                     tmem_ld32(base + g * 32, hh);
                     tmem_ld32(base + NT + g * 32, xx);
@@ -234,11 +240,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             }
             // epilogue of this tile (the MMA warp is already on the next one)
 #pragma unroll
-            for (int g = 0; g < NT / 32; ++g) {
+            for (int g = 0; g < NH / 32; ++g) {
                 float v[32], o0[32], o1[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = run[g * 32 + j];
-                epi(row, n0 + g * 32, v, o0, o1);
+                const int col0 = n0 + half * NH + g * 32;
+                epi(row, col0, v, o0, o1);
 #pragma unroll
                 for (int w = 0; w < Epilogue::kOutputs; ++w) {
                     __syncwarp();
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     __syncwarp();
                     // tiled output (the next GEMM's A operand): this warp's 32 rows x 32 columns are ONE contiguous 4 KB block;
                     // lane -> (row i*4 + lane/8, 16-byte chunk lane%8): 512 contiguous bytes per store instruction
-                    float* out = epi.out(w) + tiled_offset(m0 + quarter * 32, n0 + g * 32, epi.ld());
+                    float* out = epi.out(w) + tiled_offset(m0 + quarter * 32, col0, epi.ld());
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = i * 4 + (lane >> 3), c4 = (lane & 7) * 4;
