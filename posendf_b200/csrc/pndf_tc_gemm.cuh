@@ -162,6 +162,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     const uint32_t s = it % kStages;
                     mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);      // fresh barrier: parity 1 passes
                     uint8_t* st = smem + s * stage_bytes<NT>();
+#ifdef PNDF_TC_EXP_HALF_FEED      // bottleneck experiment (tools/tc_gemm.sh): only the hi operands travel, the MMAs run on stale lo tiles
+                    mbar_expect_tx(&full[s], stage_bytes<NT>() / 2);
+                    {
+                        const int ra = ((tile / n_tiles) * nks + ks) * kTM, rb = ((tile % n_tiles) * nks + ks) * NT;
+                        tma_load_2d(st, &maps.a_hi, 0, ra, &full[s]);
+                        tma_load_2d(st + 2 * kTM * 128, &maps.b_hi, 0, rb, &full[s]);
+                        continue;
+                    }
+#endif
                     mbar_expect_tx(&full[s], stage_bytes<NT>());
                     // operands live in TILED layout: [row tile][K block][rows of the tile][32 floats] -- every TMA box (rows x 128 bytes) is
                     // one contiguous 16 KB (8 KB) block of memory instead of 128 row segments 2-4 KB apart
@@ -178,6 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         if (lane == 0) {
             // D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * NT >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
             uint32_t it = 0, cc = 0;      // running stage / chunk counters
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int ks = 0; ks < nks; ++ks, ++it) {
@@ -192,9 +202,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
                     for (int k = 0; k < kKB / 8; ++k) {
                         const uint32_t first = (chunk_start && k == 0) ? 0u : 1u;
-                        mma_tf32(acc_hh, make_desc(a_hi + k * 32), make_desc(b_hi + k * 32), idesc, first);
-                        mma_tf32(acc_x, make_desc(a_lo + k * 32), make_desc(b_hi + k * 32), idesc, first);
-                        mma_tf32(acc_x, make_desc(a_hi + k * 32), make_desc(b_lo + k * 32), idesc, 1u);
+                        // B_hi and B_lo are adjacent in the stage and acc_x follows acc_hh in TMEM: ONE N = 2 NT instruction computes
+                        // A_hi B_hi -> acc_hh and A_hi B_lo -> acc_x and fetches A_hi once (the SS-mode operand fetch, about 64 B/clk
+                        // for tf32, is what paces these MMAs: 24 KB -> 20 KB per 8-deep K slice, -10 % GEMM time)
+                        mma_tf32(acc_hh, make_desc(a_hi + k * 32), make_desc(b_hi + k * 32), idesc2, first);
+                        mma_tf32(acc_x, make_desc(a_lo + k * 32), make_desc(b_hi + k * 32), idesc, 1u);
                     }
                     mma_commit(&empty[s]);                                               // stage s may be refilled once these MMAs retire
                     if ((ks % kStagesPerChunk) == kStagesPerChunk - 1 || ks == nks - 1) {
@@ -225,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 mbar_wait(&acc_full[p], (cc >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t base = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(p * 2 * NT + half * NH);
+#ifndef PNDF_TC_EXP_NO_DRAIN     // bottleneck experiment: accumulators are handed straight back
 #pragma unroll
                 for (int g = 0; g < NH / 32; ++g) {
                     uint32_t hh[32], xx[32];
@@ -234,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) run[g * 32 + j] += __uint_as_float(hh[j]) + __uint_as_float(xx[j]);
                 }
+#endif
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[p]);
