@@ -40,55 +40,62 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(u);
 }
 // ---- GEMM epilogues (called by the thread owning output row `row` for each 32-column group; the kernel stores the outputs)
+// The activation kind is a template parameter: with a run-time flag every element carried both branches and the epilogue of a
+// 128 x 128 tile ran to ~2 400 SASS instructions per thread -- at two drain warps per scheduler that is longer than the two
+// accumulator pairs of runway the MMA warp has, and the tensor pipe stalled on it (profiles/README.md, "epilogue exposure").
+template <bool SOFT>
 struct FwdEpi {          // z = act(acc + bias) -> hi / lo
     static constexpr int kOutputs = 2;
     const float* bias;
     float* out_hi;
     float* out_lo;
-    int ldo, soft;
+    int ldo;
     float par;           // slope (relu 0 / lrelu 0.01) or softplus beta
     __device__ float* out(int w) const { return w == 0 ? out_hi : out_lo; }
     __device__ int ld() const { return ldo; }
+    __device__ float init(int col) const { return __ldg(bias + col); }      // the running sums start at the bias (loaded while the first chunk is in flight)
     __device__ void operator()(int row, int col0, const float (&v)[32], float (&hi)[32], float (&lo)[32]) const {
-        const float inv_beta = soft ? 1.0f / par : 0.0f;
+        const float inv_beta = SOFT ? 1.0f / par : 0.0f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const float x = v[j] + __ldg(bias + col0 + j);
+            const float x = v[j];
             float dv;
-            const float z = soft ? softplus_fast(x, par, inv_beta, dv) : (x > 0.0f ? x : x * par);
+            const float z = SOFT ? softplus_fast(x, par, inv_beta, dv) : (x > 0.0f ? x : x * par);
             hi[j] = tf32_rna(z);
             lo[j] = tf32_rna(z - hi[j]);
         }
     }
 };
+template <bool SOFT>
 struct BwdEpi {          // t = acc * act'(pre) with act' recovered from the stored activation z -> hi / lo
     static constexpr int kOutputs = 2;
     const float* z_hi;
     const float* z_lo;
     float* out_hi;
     float* out_lo;
-    int ldo, soft;
+    int ldo;
     float par;
     __device__ float* out(int w) const { return w == 0 ? out_hi : out_lo; }
     __device__ int ld() const { return ldo; }
+    __device__ float init(int) const { return 0.0f; }
     __device__ void operator()(int row, int col0, const float (&v)[32], float (&hi)[32], float (&lo)[32]) const {
         const size_t off = pndf_tc::tiled_offset(row, col0, ldo);      // 32 contiguous floats (all operands are in the tiled layout)
-        const float4* zh = reinterpret_cast<const float4*>(z_hi + off);
-        const float4* zl = reinterpret_cast<const float4*>(z_lo + off);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 a = __ldg(zh + j);
-            float zz[4] = {a.x, a.y, a.z, a.w};
-            if (soft) {
-                const float4 b = __ldg(zl + j);
-                zz[0] += b.x; zz[1] += b.y; zz[2] += b.z; zz[3] += b.w;
+        for (int j = 0; j < 4; ++j) {
+            float zz[8];
+            pndf_tc::ld_global_nc_v8(z_hi + off + 8 * j, zz);
+            if (SOFT) {
+                float zl[8];
+                pndf_tc::ld_global_nc_v8(z_lo + off + 8 * j, zl);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) zz[k] += zl[k];
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float d = soft ? -expm1f(-par * zz[k]) : (zz[k] > 0.0f ? 1.0f : par);
-                const float t = v[4 * j + k] * d;
-                hi[4 * j + k] = tf32_rna(t);
-                lo[4 * j + k] = tf32_rna(t - hi[4 * j + k]);
+            for (int k = 0; k < 8; ++k) {
+                const float d = SOFT ? -expm1f(-par * zz[k]) : (zz[k] > 0.0f ? 1.0f : par);
+                const float t = v[8 * j + k] * d;
+                hi[8 * j + k] = tf32_rna(t);
+                lo[8 * j + k] = tf32_rna(t - hi[8 * j + k]);
             }
         }
     }
@@ -99,6 +106,7 @@ struct G0Epi {           // the last reverse op: dd/dz0 in fp32
     int ldo;
     __device__ float* out(int) const { return o; }
     __device__ int ld() const { return ldo; }
+    __device__ float init(int) const { return 0.0f; }
     __device__ void operator()(int, int, const float (&v)[32], float (&o0)[32], float (&)[32]) const {
 #pragma unroll
         for (int j = 0; j < 32; ++j) o0[j] = v[j];
@@ -494,12 +502,15 @@ int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
         if (tc_check(s, "tc_enc_kernel (forward) launch")) return 1;
         // ---- forward chain
         for (int l = 0; l < 6; ++l) {
-            FwdEpi fe{a.bias[l], zhi(l + 1), zlo(l + 1), zw[l + 1], dsoft ? 1 : 0, dpar};
             const float* bh = s->w_hi + s->f_off[l];
             const float* bl = s->w_lo + s->f_off[l];
             const int N = s->widths[l + 1];
-            const int rc = (N % 128 == 0) ? launch_gemm<128>(s, zhi(l), zlo(l), P, s->kpad[l], bh, bl, N, fe, st)
-                                          : launch_gemm<64>(s, zhi(l), zlo(l), P, s->kpad[l], bh, bl, N, fe, st);
+            auto fwd = [&](auto fe) {
+                return (N % 128 == 0) ? launch_gemm<128>(s, zhi(l), zlo(l), P, s->kpad[l], bh, bl, N, fe, st)
+                                      : launch_gemm<64>(s, zhi(l), zlo(l), P, s->kpad[l], bh, bl, N, fe, st);
+            };
+            const int rc = dsoft ? fwd(FwdEpi<true>{a.bias[l], zhi(l + 1), zlo(l + 1), zw[l + 1], dpar})
+                                 : fwd(FwdEpi<false>{a.bias[l], zhi(l + 1), zlo(l + 1), zw[l + 1], dpar});
             if (rc) return 1;
         }
         HeadParams hp{};
@@ -518,8 +529,8 @@ int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
             const int K = s->widths[l + 1], N = s->ninpad[l];
             int rc;
             if (l > 0) {
-                BwdEpi be{zhi(l), zlo(l), thi(l - 1), tlo(l - 1), zw[l], dsoft ? 1 : 0, dpar};
-                rc = launch_gemm<128>(s, thi(l), tlo(l), P, K, bh, bl, N, be, st);
+                rc = dsoft ? launch_gemm<128>(s, thi(l), tlo(l), P, K, bh, bl, N, BwdEpi<true>{zhi(l), zlo(l), thi(l - 1), tlo(l - 1), zw[l], dpar}, st)
+                           : launch_gemm<128>(s, thi(l), tlo(l), P, K, bh, bl, N, BwdEpi<false>{zhi(l), zlo(l), thi(l - 1), tlo(l - 1), zw[l], dpar}, st);
             } else {
                 G0Epi ge{g0, 128};
                 rc = launch_gemm<128>(s, thi(0), tlo(0), P, K, bh, bl, N, ge, st);

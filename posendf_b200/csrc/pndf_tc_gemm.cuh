@@ -69,6 +69,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// 256-bit global store / load (sm_100: STG.256 / LDG.256), 32-byte aligned
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_v8(const float* p, float* v) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -101,9 +112,8 @@ __host__ __device__ __forceinline__ size_t tiled_offset(long long r, int c, int 
 
 template <int NT>
 __host__ __device__ constexpr int stage_bytes() { return 2 * kTM * 128 + 2 * NT * 128; }
-constexpr int kStageRow = 33;            // padded row of the per-warp output staging tile (32 x 32 floats)
 template <int NT>
-__host__ __device__ constexpr int smem_bytes() { return kStages * stage_bytes<NT>() + 1024 + 256 + kDrainWarps * 32 * kStageRow * 4; }
+__host__ __device__ constexpr int smem_bytes() { return kStages * stage_bytes<NT>() + 1024 + 256; }
 
 struct GemmMaps {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -111,10 +121,12 @@ struct GemmMaps {
 
 // Epilogue functor interface:
 //   static constexpr int kOutputs            1 or 2 output arrays
+//   float init(int col) const                the value the running sum of column col starts from (a bias, or 0)
 //   void operator()(int row, int col0, const float (&v)[32], float (&o0)[32], float (&o1)[32]) const
 //                                            called by the thread that owns `row` for every 32-column group of its tile
 //   float* out(int which) const, int ld()    the output arrays (row-major, row length ld)
-// The kernel stores the outputs itself, coalesced through a per-warp shared-memory staging tile.
+// The kernel stores the outputs itself: in the tiled layout a thread's 32 columns of its row are 128 contiguous bytes = four 256-bit
+// stores (STG.256, whole 32-byte sectors).
 //
 // Persistent: gridDim.x CTAs walk the (m_tile, n_tile) list (n fastest: the CTAs that share an A tile run together).  The running
 // sums live in the drain warps' registers, so the TMEM accumulator pairs are free as soon as a tile's last chunk is drained: the
@@ -131,7 +143,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     uint64_t* acc_full = bars + 2 * kStages; // [2]
     uint64_t* acc_empty = acc_full + 2;      // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* staging = reinterpret_cast<float*>(smem + kStages * stage_bytes<NT>() + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nks = K / kKB;
     constexpr int kStagesPerChunk = kChunkK / kKB;
@@ -224,14 +235,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         const int quarter = warp & 3;                       // TMEM lanes [32 q, 32 q + 32) are this warp's
         const int half = (warp - 2) >> 2;                   // columns [half * NT / 2, (half + 1) * NT / 2)
         constexpr int NH = NT / 2;
-        float* stg = staging + (warp - 2) * (32 * kStageRow);
         uint32_t cc = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * NT;
             const int row = m0 + quarter * 32 + lane;
             float run[NH];
 #pragma unroll
-            for (int j = 0; j < NH; ++j) run[j] = 0.0f;
+            for (int j = 0; j < NH; ++j) run[j] = epi.init(n0 + half * NH + j);
             for (int c = 0; c < nchunks; ++c, ++cc) {
                 const uint32_t p = cc & 1;
                 mbar_wait(&acc_full[p], (cc >> 1) & 1);
@@ -253,6 +263,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 if (lane == 0) mbar_arrive(&acc_empty[p]);
             }
             // epilogue of this tile (the MMA warp is already on the next one)
+#ifdef PNDF_TC_EXP_NO_EPI       // bottleneck experiment: nothing is computed or stored after the drain
+            if (run[0] != 123.456f) continue;
+#endif
 #pragma unroll
             for (int g = 0; g < NH / 32; ++g) {
                 float v[32], o0[32], o1[32];
@@ -262,19 +275,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 epi(row, col0, v, o0, o1);
 #pragma unroll
                 for (int w = 0; w < Epilogue::kOutputs; ++w) {
-                    __syncwarp();
+                    // tiled output (the next GEMM's A operand): the 32 columns of this thread's row are 128 contiguous bytes.  (Staging
+                    // the 32 x 32 block through shared memory for 512-byte-per-instruction stores cost 72 memory instructions per block
+                    // and left the epilogue -- two warps per scheduler -- exposed: 2.73 -> 2.67 ms per 65 536-pose step without it.)
+                    float* out = epi.out(w) + tiled_offset(row, col0, epi.ld());
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) stg[lane * kStageRow + j] = (w == 0) ? o0[j] : o1[j];
-                    __syncwarp();
-                    // tiled output (the next GEMM's A operand): this warp's 32 rows x 32 columns are ONE contiguous 4 KB block;
-                    // lane -> (row i*4 + lane/8, 16-byte chunk lane%8): 512 contiguous bytes per store instruction
-                    float* out = epi.out(w) + tiled_offset(m0 + quarter * 32, col0, epi.ld());
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = i * 4 + (lane >> 3), c4 = (lane & 7) * 4;
-                        const float* sp = stg + r * kStageRow + c4;
-                        *reinterpret_cast<float4*>(out + r * 32 + c4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
-                    }
+                    for (int i = 0; i < 4; ++i) st_global_v8(out + 8 * i, w == 0 ? &o0[8 * i] : &o1[8 * i]);
                 }
             }
         }
