@@ -51,7 +51,8 @@ struct FwdEpi {          // z = act(acc + bias) -> hi / lo
     float* out_lo;
     int ldo;
     float par;           // slope (relu 0 / lrelu 0.01) or softplus beta
-    __device__ float* out(int w) const { return w == 0 ? out_hi : out_lo; }
+    __host__ __device__ float* out(int w) const { return w == 0 ? out_hi : out_lo; }
+    const float* out_host(int w) const { return w == 0 ? out_hi : out_lo; }
     __device__ int ld() const { return ldo; }
     __device__ float init(int col) const { return __ldg(bias + col); }      // the running sums start at the bias (loaded while the first chunk is in flight)
     __device__ void operator()(int row, int col0, const float (&v)[32], float (&hi)[32], float (&lo)[32]) const {
@@ -75,7 +76,8 @@ struct BwdEpi {          // t = acc * act'(pre) with act' recovered from the sto
     float* out_lo;
     int ldo;
     float par;
-    __device__ float* out(int w) const { return w == 0 ? out_hi : out_lo; }
+    __host__ __device__ float* out(int w) const { return w == 0 ? out_hi : out_lo; }
+    const float* out_host(int w) const { return w == 0 ? out_hi : out_lo; }
     __device__ int ld() const { return ldo; }
     __device__ float init(int) const { return 0.0f; }
     __device__ void operator()(int row, int col0, const float (&v)[32], float (&hi)[32], float (&lo)[32]) const {
@@ -104,7 +106,8 @@ struct G0Epi {           // the last reverse op: dd/dz0 in fp32
     static constexpr int kOutputs = 1;
     float* o;
     int ldo;
-    __device__ float* out(int) const { return o; }
+    __host__ __device__ float* out(int) const { return o; }
+    const float* out_host(int) const { return o; }
     __device__ int ld() const { return ldo; }
     __device__ float init(int) const { return 0.0f; }
     __device__ void operator()(int, int, const float (&v)[32], float (&o0)[32], float (&)[32]) const {
@@ -463,6 +466,8 @@ static int launch_gemm(TcState* s, const float* a_hi, const float* a_lo, long lo
     if (!make_map(&maps.a_hi, a_hi, P, K, pndf_tc::kTM) || !make_map(&maps.a_lo, a_lo, P, K, pndf_tc::kTM) || !make_map(&maps.b_hi, b_hi, N, K, NT) ||
         !make_map(&maps.b_lo, b_lo, N, K, NT))
         return tc_fail(s, "cuTensorMapEncodeTiled failed");
+    for (int w = 0; w < Epi::kOutputs; ++w)
+        if (!make_out_map(&maps.out[w], epi.out_host(w), P, epi.ldo)) return tc_fail(s, "cuTensorMapEncodeTiled failed (output)");
     auto kern = tc_gemm_kernel<NT, Epi>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pndf_tc::smem_bytes<NT>()) != cudaSuccess)
         return tc_fail(s, "cudaFuncSetAttribute failed");

@@ -56,6 +56,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
                      smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                  : "memory");
 }
+// TMA tensor store of one box from (swizzled) shared memory; bulk-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
 }
@@ -112,11 +122,13 @@ __host__ __device__ __forceinline__ size_t tiled_offset(long long r, int c, int 
 
 template <int NT>
 __host__ __device__ constexpr int stage_bytes() { return 2 * kTM * 128 + 2 * NT * 128; }
+constexpr int kOutStage = 32 * 128;      // per drain warp: one 32-row x 32-column output block, 128-byte swizzled, the source of a TMA store
 template <int NT>
-__host__ __device__ constexpr int smem_bytes() { return kStages * stage_bytes<NT>() + 1024 + 256; }
+__host__ __device__ constexpr int smem_bytes() { return kStages * stage_bytes<NT>() + kDrainWarps * kOutStage + 1024 + 256; }
 
 struct GemmMaps {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    CUtensorMap out[2];      // the output arrays (tiled layout), box = 32 rows x 32 columns (one drain warp's block)
 };
 
 // Epilogue functor interface:
@@ -125,8 +137,10 @@ struct GemmMaps {
 //   void operator()(int row, int col0, const float (&v)[32], float (&o0)[32], float (&o1)[32]) const
 //                                            called by the thread that owns `row` for every 32-column group of its tile
 //   float* out(int which) const, int ld()    the output arrays (row-major, row length ld)
-// The kernel stores the outputs itself: in the tiled layout a thread's 32 columns of its row are 128 contiguous bytes = four 256-bit
-// stores (STG.256, whole 32-byte sectors).
+// The kernel stores the outputs itself: a drain warp writes its 32 rows x 32 columns into a 128-byte-swizzled 4 KB staging block
+// (conflict-free STS.128) and ONE TMA tensor store moves the block -- 4 contiguous KB of the tiled layout -- to global memory.
+// (Per-thread STG.256 of a row's 128 bytes touches 32 lines per instruction: the LSU queue (`stall_lg`) held 38 % of the drain
+// warps' samples and the epilogue outlasted the two accumulator pairs of runway the MMA warp has.)
 //
 // Persistent: gridDim.x CTAs walk the (m_tile, n_tile) list (n fastest: the CTAs that share an A tile run together).  The running
 // sums live in the drain warps' registers, so the TMEM accumulator pairs are free as soon as a tile's last chunk is drained: the
@@ -137,7 +151,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                                                               Epilogue epi) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes<NT>());
+    uint8_t* out_stage = smem + kStages * stage_bytes<NT>();       // [kDrainWarps][kOutStage], 1024-byte aligned blocks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kDrainWarps * kOutStage);
     uint64_t* full = bars;                   // [kStages]
     uint64_t* empty = bars + kStages;        // [kStages]
     uint64_t* acc_full = bars + 2 * kStages; // [2]
@@ -235,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         const int quarter = warp & 3;                       // TMEM lanes [32 q, 32 q + 32) are this warp's
         const int half = (warp - 2) >> 2;                   // columns [half * NT / 2, (half + 1) * NT / 2)
         constexpr int NH = NT / 2;
+        const uint32_t stg = smem_u32(out_stage + (warp - 2) * kOutStage);
         uint32_t cc = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * NT;
@@ -275,15 +291,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                 epi(row, col0, v, o0, o1);
 #pragma unroll
                 for (int w = 0; w < Epilogue::kOutputs; ++w) {
-                    // tiled output (the next GEMM's A operand): the 32 columns of this thread's row are 128 contiguous bytes.  (Staging
-                    // the 32 x 32 block through shared memory for 512-byte-per-instruction stores cost 72 memory instructions per block
-                    // and left the epilogue -- two warps per scheduler -- exposed: 2.73 -> 2.67 ms per 65 536-pose step without it.)
-                    float* out = epi.out(w) + tiled_offset(row, col0, epi.ld());
+                    // tiled output (the next GEMM's A operand): this warp's 32 rows x 32 columns are ONE contiguous 4 KB block = one TMA
+                    // box.  Row `lane` of the staging block, 16-byte chunk c at position c ^ (lane & 7): the 128-byte swizzle the tensor
+                    // map undoes on the way out, and conflict-free for the warp's STS.128.
+                    tma_store_wait_read();              // the previous store of this warp has finished reading the block
+                    __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) st_global_v8(out + 8 * i, w == 0 ? &o0[8 * i] : &o1[8 * i]);
+                    for (int c = 0; c < 8; ++c) {
+                        const float* o = (w == 0) ? &o0[4 * c] : &o1[4 * c];
+                        st_shared_v4(stg + lane * 128 + ((c ^ (lane & 7)) << 4), o[0], o[1], o[2], o[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int c1 = ((m0 / kTM) * (epi.ld() / 32) + col0 / 32) * kTM + quarter * 32;
+                        tma_store_2d(&maps.out[w], 0, c1, reinterpret_cast<const void*>(out_stage + (warp - 2) * kOutStage));
+                        tma_store_commit();
+                    }
                 }
             }
         }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this warp's last stores have landed before the CTA retires
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -318,5 +346,8 @@ inline bool make_map(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+
+// output map of a GEMM: the tiled [rows][ld] array, one drain warp's 32 x 32 block per store
+inline bool make_out_map(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t ld) { return make_map(tm, base, rows, ld, 32); }
 
 }  // namespace pndf_tc
