@@ -51,10 +51,16 @@ struct FwdEpi {          // z = act(acc + bias) -> hi / lo
     float* out_lo;
     int ldo;
     float par;           // slope (relu 0 / lrelu 0.01) or softplus beta
+    uint32_t* mask;      // piecewise-linear kinds: bit j of word [tiled_offset(row, col0) / 32] = (pre-activation of column col0 + j > 0),
+                         // all the reverse pass needs (128 coalesced bytes per warp instead of re-reading 4 KB of z); may be null
     __host__ __device__ float* out(int w) const { return w == 0 ? out_hi : out_lo; }
     const float* out_host(int w) const { return w == 0 ? out_hi : out_lo; }
     __device__ int ld() const { return ldo; }
-    __device__ float init(int col) const { return __ldg(bias + col); }      // the running sums start at the bias (loaded while the first chunk is in flight)
+    // the running sums start at the bias (16-byte aligned: csrc/pndf_capi.cu pads every small-parameter block)
+    __device__ void init4(int col, float* r) const {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+        r[0] = b.x; r[1] = b.y; r[2] = b.z; r[3] = b.w;
+    }
     __device__ void operator()(int row, int col0, const float (&v)[32], float (&hi)[32], float (&lo)[32]) const {
         const float inv_beta = SOFT ? 1.0f / par : 0.0f;
 #pragma unroll
@@ -64,6 +70,12 @@ struct FwdEpi {          // z = act(acc + bias) -> hi / lo
             const float z = SOFT ? softplus_fast(x, par, inv_beta, dv) : (x > 0.0f ? x : x * par);
             hi[j] = tf32_rna(z);
             lo[j] = tf32_rna(z - hi[j]);
+        }
+        if (!SOFT && mask) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.0f ? 1u : 0u) << j;
+            mask[pndf_tc::tiled_offset(row, col0, ldo) >> 5] = bits;      // consecutive lanes = consecutive rows = consecutive words
         }
     }
 };
@@ -76,25 +88,31 @@ struct BwdEpi {          // t = acc * act'(pre) with act' recovered from the sto
     float* out_lo;
     int ldo;
     float par;
+    const uint32_t* mask;      // piecewise-linear kinds: the forward epilogue's sign bits (see FwdEpi); softplus reads z instead
     __host__ __device__ float* out(int w) const { return w == 0 ? out_hi : out_lo; }
     const float* out_host(int w) const { return w == 0 ? out_hi : out_lo; }
     __device__ int ld() const { return ldo; }
-    __device__ float init(int) const { return 0.0f; }
+    __device__ void init4(int, float* r) const { r[0] = r[1] = r[2] = r[3] = 0.0f; }
     __device__ void operator()(int row, int col0, const float (&v)[32], float (&hi)[32], float (&lo)[32]) const {
         const size_t off = pndf_tc::tiled_offset(row, col0, ldo);      // 32 contiguous floats (all operands are in the tiled layout)
+        if (!SOFT) {
+            const uint32_t bits = __ldg(mask + (off >> 5));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float t = v[j] * (((bits >> j) & 1u) ? 1.0f : par);
+                hi[j] = tf32_rna(t);
+                lo[j] = tf32_rna(t - hi[j]);
+            }
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float zz[8];
+            float zz[8], zl[8];
             pndf_tc::ld_global_nc_v8(z_hi + off + 8 * j, zz);
-            if (SOFT) {
-                float zl[8];
-                pndf_tc::ld_global_nc_v8(z_lo + off + 8 * j, zl);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) zz[k] += zl[k];
-            }
+            pndf_tc::ld_global_nc_v8(z_lo + off + 8 * j, zl);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const float d = SOFT ? -expm1f(-par * zz[k]) : (zz[k] > 0.0f ? 1.0f : par);
+                const float d = -expm1f(-par * (zz[k] + zl[k]));
                 const float t = v[8 * j + k] * d;
                 hi[8 * j + k] = tf32_rna(t);
                 lo[8 * j + k] = tf32_rna(t - hi[8 * j + k]);
@@ -109,7 +127,7 @@ struct G0Epi {           // the last reverse op: dd/dz0 in fp32
     __host__ __device__ float* out(int) const { return o; }
     const float* out_host(int) const { return o; }
     __device__ int ld() const { return ldo; }
-    __device__ float init(int) const { return 0.0f; }
+    __device__ void init4(int, float* r) const { r[0] = r[1] = r[2] = r[3] = 0.0f; }
     __device__ void operator()(int, int, const float (&v)[32], float (&o0)[32], float (&)[32]) const {
 #pragma unroll
         for (int j = 0; j < 32; ++j) o0[j] = v[j];
@@ -377,7 +395,7 @@ struct TcState {
     // activations for `cap` poses (multiple of 128): forward z_0..z_6 (hi, lo), reverse t_5..t_0 (hi, lo), g0, dist
     long long cap = 0;
     float* act = nullptr;
-    long long z_off[7], t_off[6], g0_off = 0, dist_off = 0, act_floats = 0;
+    long long z_off[7], t_off[6], g0_off = 0, dist_off = 0, mask_off[7] = {0, 0, 0, 0, 0, 0, 0}, act_floats = 0;
     int num_sms = 148;
     std::string err;
 };
@@ -451,6 +469,7 @@ static int ensure_act(TcState* s, long long B) {
     for (int l = 0; l < 6; ++l) { s->t_off[l] = off; off += 2 * P * tw[l]; }
     s->g0_off = off; off += P * 128;
     s->dist_off = off; off += P;
+    for (int l = 1; l <= 5; ++l) { s->mask_off[l] = off; off += P * zw[l] / 32; }      // sign bits of the pre-activations of z_1 .. z_5
     if (cudaMalloc(&s->act, off * sizeof(float)) != cudaSuccess) return tc_fail(s, "tensor-core path: cannot allocate the activation buffers");
     if (cudaMemset(s->act, 0, off * sizeof(float)) != cudaSuccess) return tc_fail(s, "cudaMemset failed");
     s->cap = P;
@@ -489,6 +508,7 @@ int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
     auto zlo = [&](int l) { return s->act + s->z_off[l] + P * zw[l]; };
     auto thi = [&](int l) { return s->act + s->t_off[l]; };
     auto tlo = [&](int l) { return s->act + s->t_off[l] + P * s->widths[l + 1]; };
+    auto maskp = [&](int l) { return reinterpret_cast<uint32_t*>(s->act + s->mask_off[l]); };
     float* g0 = s->act + s->g0_off;
     float* dkeep = s->act + s->dist_off;
     cudaFuncSetAttribute(tc_enc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmTotal);
@@ -514,8 +534,9 @@ int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
                 return (N % 128 == 0) ? launch_gemm<128>(s, zhi(l), zlo(l), P, s->kpad[l], bh, bl, N, fe, st)
                                       : launch_gemm<64>(s, zhi(l), zlo(l), P, s->kpad[l], bh, bl, N, fe, st);
             };
-            const int rc = dsoft ? fwd(FwdEpi<true>{a.bias[l], zhi(l + 1), zlo(l + 1), zw[l + 1], dpar})
-                                 : fwd(FwdEpi<false>{a.bias[l], zhi(l + 1), zlo(l + 1), zw[l + 1], dpar});
+            uint32_t* mk = (l < 5 && a.want_grad) ? maskp(l + 1) : nullptr;
+            const int rc = dsoft ? fwd(FwdEpi<true>{a.bias[l], zhi(l + 1), zlo(l + 1), zw[l + 1], dpar, nullptr})
+                                 : fwd(FwdEpi<false>{a.bias[l], zhi(l + 1), zlo(l + 1), zw[l + 1], dpar, mk});
             if (rc) return 1;
         }
         HeadParams hp{};
@@ -534,8 +555,8 @@ int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
             const int K = s->widths[l + 1], N = s->ninpad[l];
             int rc;
             if (l > 0) {
-                rc = dsoft ? launch_gemm<128>(s, thi(l), tlo(l), P, K, bh, bl, N, BwdEpi<true>{zhi(l), zlo(l), thi(l - 1), tlo(l - 1), zw[l], dpar}, st)
-                           : launch_gemm<128>(s, thi(l), tlo(l), P, K, bh, bl, N, BwdEpi<false>{zhi(l), zlo(l), thi(l - 1), tlo(l - 1), zw[l], dpar}, st);
+                rc = dsoft ? launch_gemm<128>(s, thi(l), tlo(l), P, K, bh, bl, N, BwdEpi<true>{zhi(l), zlo(l), thi(l - 1), tlo(l - 1), zw[l], dpar, nullptr}, st)
+                           : launch_gemm<128>(s, thi(l), tlo(l), P, K, bh, bl, N, BwdEpi<false>{zhi(l), zlo(l), thi(l - 1), tlo(l - 1), zw[l], dpar, maskp(l)}, st);
             } else {
                 G0Epi ge{g0, 128};
                 rc = launch_gemm<128>(s, thi(0), tlo(0), P, K, bh, bl, N, ge, st);

@@ -133,7 +133,7 @@ struct GemmMaps {
 
 // Epilogue functor interface:
 //   static constexpr int kOutputs            1 or 2 output arrays
-//   float init(int col) const                the value the running sum of column col starts from (a bias, or 0)
+//   void init4(int col, float* r) const      the values the running sums of columns col .. col + 3 start from (a bias, or 0)
 //   void operator()(int row, int col0, const float (&v)[32], float (&o0)[32], float (&o1)[32]) const
 //                                            called by the thread that owns `row` for every 32-column group of its tile
 //   float* out(int which) const, int ld()    the output arrays (row-major, row length ld)
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             const int row = m0 + quarter * 32 + lane;
             float run[NH];
 #pragma unroll
-            for (int j = 0; j < NH; ++j) run[j] = epi.init(n0 + half * NH + j);
+            for (int j = 0; j < NH; j += 4) epi.init4(n0 + half * NH + j, &run[j]);
             for (int c = 0; c < nchunks; ++c, ++cc) {
                 const uint32_t p = cc & 1;
                 mbar_wait(&acc_full[p], (cc >> 1) & 1);

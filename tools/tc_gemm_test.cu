@@ -16,7 +16,7 @@ struct StoreEpi {
     int ldd;
     __device__ float* out(int) const { return D; }
     __device__ int ld() const { return ldd; }
-    __device__ float init(int) const { return 0.0f; }
+    __device__ void init4(int, float* r) const { r[0] = r[1] = r[2] = r[3] = 0.0f; }
     __device__ void operator()(int, int, const float (&v)[32], float (&o0)[32], float (&)[32]) const {
 #pragma unroll
         for (int j = 0; j < 32; ++j) o0[j] = v[j];
@@ -32,7 +32,7 @@ struct SplitEpi {
     int ldd;
     __device__ float* out(int w) const { return w == 0 ? hi_ : lo_; }
     __device__ int ld() const { return ldd; }
-    __device__ float init(int) const { return 0.0f; }
+    __device__ void init4(int, float* r) const { r[0] = r[1] = r[2] = r[3] = 0.0f; }
     __device__ void operator()(int, int col0, const float (&v)[32], float (&hi)[32], float (&lo)[32]) const {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
