@@ -187,6 +187,8 @@ struct EncParams {
     float* z0_hi;            // [P][z0_ld]
     float* z0_lo;
     const float* g0;         // [P][128] (reverse kernel)
+    const float* feat;       // [P][128] fp32 encoder features of the forward kernel (reverse kernel; tiled layout)
+    float* feat_out;         // same buffer, written by the forward kernel when a reverse pass follows
     const float* dist;       // [B]      (reverse kernel: d of this step)
     float* pose_out;         // [B][84] or nullptr
     float* grad;             // [B][84] or nullptr
@@ -195,23 +197,24 @@ struct EncParams {
     int z0_ld, normalise, use_enc, enc_act, do_step, renorm, n_peers;
     float enc_beta;
 };
+// shared-memory layout: the forward kernel needs no gradient buffer (5 CTAs per SM), the reverse kernel no encoder recomputation
+// (3 CTAs per SM): both are latency-bound prologue -> tree walk -> epilogue pipelines, occupancy is what overlaps them
 constexpr int kEncSmX = 0;                               // [128][32] features (swizzled, as the fused kernel)
-constexpr int kEncSmY = kEncSmX + 128 * 32 * 4;          // [224][32] gradient buffer: rows [0,128) dd/dz0, rows [128,212) qbar
-constexpr int kEncSmW = kEncSmY + 224 * 32 * 4;          // encoder weights
-constexpr int kEncSmXs = kEncSmW + ((kEncFloats * 4 + 127) / 128) * 128;
-constexpr int kEncSmQs = kEncSmXs + kTileM * kXS * 4;
-constexpr int kEncSmNrm = kEncSmQs + kTileM * kXS * 4;
-constexpr int kEncSmTotal = kEncSmNrm + 4 * 32 * 4;
+template <bool REVERSE> __host__ __device__ constexpr int enc_sm_y() { return kEncSmX + 128 * 32 * 4; }      // reverse: [224][32] gradients: rows [0,128) dd/dz0 (then the
+                                                                                         // projected pose), rows [128,212) qbar
+template <bool REVERSE> __host__ __device__ constexpr int enc_sm_w() { return enc_sm_y<REVERSE>() + (REVERSE ? 224 * 32 * 4 : 0); }
+template <bool REVERSE> __host__ __device__ constexpr int enc_sm_qs() { return enc_sm_w<REVERSE>() + ((kEncFloats * 4 + 127) / 128) * 128; }
+template <bool REVERSE> __host__ __device__ constexpr int enc_sm_nrm() { return enc_sm_qs<REVERSE>() + kTileM * kXS * 4; }
+template <bool REVERSE> __host__ __device__ constexpr int enc_sm_total() { return enc_sm_nrm<REVERSE>() + 4 * 32 * 4; }
 
 template <bool ESOFT, bool REVERSE>
 __global__ void __launch_bounds__(256) tc_enc_kernel(const EncParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* X = reinterpret_cast<float*>(smem + kEncSmX);
-    float* Y = reinterpret_cast<float*>(smem + kEncSmY);
-    float* encw = reinterpret_cast<float*>(smem + kEncSmW);
-    float* xs = reinterpret_cast<float*>(smem + kEncSmXs);
-    float* qs = reinterpret_cast<float*>(smem + kEncSmQs);
-    float* nrm = reinterpret_cast<float*>(smem + kEncSmNrm);
+    float* Y = reinterpret_cast<float*>(smem + enc_sm_y<REVERSE>());
+    float* encw = reinterpret_cast<float*>(smem + enc_sm_w<REVERSE>());
+    float* qs = reinterpret_cast<float*>(smem + enc_sm_qs<REVERSE>());
+    float* nrm = reinterpret_cast<float*>(smem + enc_sm_nrm<REVERSE>());
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long pose0 = (long long)blockIdx.x * kTileM;
     const int nvalid = (int)min((long long)kTileM, p.B - pose0);
@@ -219,13 +222,15 @@ __global__ void __launch_bounds__(256) tc_enc_kernel(const EncParams p) {
     enc.l = lane & 7; enc.base = lane & 24; enc.m = warp * 4 + (lane >> 3);
     const float apar = ESOFT ? p.enc_beta : ((p.enc_act == ACT_RELU) ? 0.0f : 0.01f);
 
-    for (int idx = tid; idx < kTileM * 84; idx += 256) xs[idx] = (idx < nvalid * 84) ? __ldg(p.pose + pose0 * 84 + idx) : 0.0f;
+    for (int idx = tid; idx < kTileM * 84; idx += 256) qs[idx] = (idx < nvalid * 84) ? __ldg(p.pose + pose0 * 84 + idx) : 0.0f;      // raw x, scaled in place
     if (p.use_enc)
         for (int i = tid; i < kEncFloats; i += 256) encw[i] = __ldg(p.encw + i);
-    if (REVERSE) {      // dd/dz0 of this tile, pose-major in HBM -> [feature][pose] rows [0, 128) of Y
+    if (REVERSE) {      // dd/dz0 and the features of this tile, pose-major in HBM -> [feature][pose]
         for (int idx = tid; idx < kTileM * 128; idx += 256) {
             const int m = idx >> 7, f = idx & 127;
-            Y[swz(f, m)] = (m < nvalid) ? __ldg(p.g0 + pndf_tc::tiled_offset(pose0 + m, f, 128)) : 0.0f;
+            const size_t off = pndf_tc::tiled_offset(pose0 + m, f, 128);
+            Y[swz(f, m)] = (m < nvalid) ? __ldg(p.g0 + off) : 0.0f;
+            if (p.use_enc) X[swz(f, m)] = (m < nvalid) ? __ldg(p.feat + off) : 0.0f;
         }
     }
     __syncthreads();
@@ -235,41 +240,43 @@ __global__ void __launch_bounds__(256) tc_enc_kernel(const EncParams p) {
         if (p.normalise) {
             float sq = 0.0f;
             for (int j = hf; j < 21; j += 2) {
-                const float x = xs[enc.m * kXS + j * 4 + cpt];
+                const float x = qs[enc.m * kXS + j * 4 + cpt];
                 sq = fmaf(x, x, sq);
             }
             sq += __shfl_xor_sync(0xffffffffu, sq, 4);
             const float n = fmaxf(sqrtf(sq), 1e-12f);
             if (hf == 0) nrm[cpt * 32 + enc.m] = n;
-            for (int j = hf; j < 21; j += 2) qs[enc.m * kXS + j * 4 + cpt] = xs[enc.m * kXS + j * 4 + cpt] / n;
-        } else {
-            for (int j = hf; j < 21; j += 2) qs[enc.m * kXS + j * 4 + cpt] = xs[enc.m * kXS + j * 4 + cpt];
+            for (int j = hf; j < 21; j += 2) qs[enc.m * kXS + j * 4 + cpt] = qs[enc.m * kXS + j * 4 + cpt] / n;
         }
         __syncwarp();
-        if (p.use_enc) {
-            encoder_forward<ESOFT>(encw, qs, X, nullptr, enc, apar);
-            if (enc.l < 2) X[swz(126 + enc.l, enc.m)] = 0.0f;
-        } else {
-            for (int e = enc.l; e < 128; e += 8) X[swz(e, enc.m)] = (e < 84) ? qs[enc.m * kXS + e] : 0.0f;
+        if (!REVERSE) {
+            if (p.use_enc) {
+                encoder_forward<ESOFT>(encw, qs, X, nullptr, enc, apar);
+                if (enc.l < 2) X[swz(126 + enc.l, enc.m)] = 0.0f;
+            } else {
+                for (int e = enc.l; e < 128; e += 8) X[swz(e, enc.m)] = (e < 84) ? qs[enc.m * kXS + e] : 0.0f;
+            }
         }
     }
-    __syncthreads();
     if (!REVERSE) {
-        // z0 -> pose-major tf32 hi / lo rows of width z0_ld (128 with the encoder, 96 without)
+        __syncthreads();
+        // z0 -> pose-major tf32 hi / lo rows of width z0_ld (128 with the encoder, 96 without) + the fp32 features for the reverse kernel
         const int cols = p.z0_ld;
         for (int idx = tid; idx < kTileM * (cols / 4); idx += 256) {
             const int m = idx / (cols / 4), c4 = (idx - m * (cols / 4)) * 4;
             if (m >= nvalid) continue;
-            float h[4], l[4];
+            float z[4], h[4], l[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float z = X[swz(c4 + k, m)];
-                h[k] = tf32_rna(z);
-                l[k] = tf32_rna(z - h[k]);
+                z[k] = X[swz(c4 + k, m)];
+                h[k] = tf32_rna(z[k]);
+                l[k] = tf32_rna(z[k] - h[k]);
             }
             const size_t off = pndf_tc::tiled_offset(pose0 + m, c4, cols);
             *reinterpret_cast<float4*>(p.z0_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<float4*>(p.z0_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+            if (p.feat_out != nullptr && p.use_enc)
+                *reinterpret_cast<float4*>(p.feat_out + pndf_tc::tiled_offset(pose0 + m, c4, 128)) = make_float4(z[0], z[1], z[2], z[3]);
         }
         return;
     }
@@ -291,38 +298,39 @@ __global__ void __launch_bounds__(256) tc_enc_kernel(const EncParams p) {
             dot += __shfl_xor_sync(0xffffffffu, dot, 4);
             if (n <= 1e-12f) dot = 0.0f;
         }
+        __syncwarp();
         for (int j = hf; j < 21; j += 2) {
             const int e = j * 4 + cpt;
-            const float x = xs[m * kXS + e];
             float g = Y[swz(128 + e, m)];
             if (p.normalise) g = (g - qs[m * kXS + e] * dot) / n;
             Y[swz(128 + e, m)] = g;
-            if (p.do_step) xs[m * kXS + e] = __fsub_rn(x, __fmul_rn(d, g));
+            if (p.do_step) {      // the projected pose takes the place of dd/dz0 (rows [0, 84) of this warp's columns)
+                const float x = (m < nvalid) ? __ldg(p.pose + (pose0 + m) * 84 + e) : 0.0f;
+                Y[swz(e, m)] = __fsub_rn(x, __fmul_rn(d, g));
+            }
         }
         if (p.do_step && p.renorm) {
             __syncwarp();
             for (int j = enc.l; j < 21; j += 8) {
                 float sq = 0.0f;
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) sq = fmaf(xs[m * kXS + j * 4 + c4], xs[m * kXS + j * 4 + c4], sq);
+                for (int c4 = 0; c4 < 4; ++c4) sq = fmaf(Y[swz(j * 4 + c4, m)], Y[swz(j * 4 + c4, m)], sq);
                 const float inv = 1.0f / sqrtf(sq);
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) xs[m * kXS + j * 4 + c4] *= inv;
+                for (int c4 = 0; c4 < 4; ++c4) Y[swz(j * 4 + c4, m)] *= inv;
             }
         }
     }
     __syncthreads();
-    if (p.grad != nullptr)
-        for (int idx = tid; idx < nvalid * 84; idx += 256) {
-            const int m = idx / 84, e = idx - m * 84;
-            p.grad[pose0 * 84 + idx] = Y[swz(128 + e, m)];
+    for (int idx = tid; idx < nvalid * 84; idx += 256) {
+        const int m = idx / 84, e = idx - m * 84;
+        if (p.grad != nullptr) p.grad[pose0 * 84 + idx] = Y[swz(128 + e, m)];
+        if (p.pose_out != nullptr) {
+            const float v = Y[swz(e, m)];
+            p.pose_out[pose0 * 84 + idx] = v;
+            for (int r = 0; r < p.n_peers; ++r) p.peer_pose[r][pose0 * 84 + idx] = v;
         }
-    if (p.pose_out != nullptr)
-        for (int i4 = tid; i4 < nvalid * 21; i4 += 256) {
-            const float4 v = reinterpret_cast<const float4*>(xs)[i4];
-            reinterpret_cast<float4*>(p.pose_out + pose0 * 84)[i4] = v;
-            for (int r = 0; r < p.n_peers; ++r) reinterpret_cast<float4*>(p.peer_pose[r] + pose0 * 84)[i4] = v;
-        }
+    }
 }
 
 // ---- layer 6 + output activation + seed of the reverse chain, one thread per pose
@@ -395,7 +403,7 @@ struct TcState {
     // activations for `cap` poses (multiple of 128): forward z_0..z_6 (hi, lo), reverse t_5..t_0 (hi, lo), g0, dist
     long long cap = 0;
     float* act = nullptr;
-    long long z_off[7], t_off[6], g0_off = 0, dist_off = 0, mask_off[7] = {0, 0, 0, 0, 0, 0, 0}, act_floats = 0;
+    long long z_off[7], t_off[6], g0_off = 0, dist_off = 0, mask_off[7] = {0, 0, 0, 0, 0, 0, 0}, feat_off = 0, act_floats = 0;
     int num_sms = 148;
     std::string err;
 };
@@ -469,6 +477,7 @@ static int ensure_act(TcState* s, long long B) {
     for (int l = 0; l < 6; ++l) { s->t_off[l] = off; off += 2 * P * tw[l]; }
     s->g0_off = off; off += P * 128;
     s->dist_off = off; off += P;
+    s->feat_off = off; off += P * 128;                                                  // fp32 encoder features (forward -> reverse kernel)
     for (int l = 1; l <= 5; ++l) { s->mask_off[l] = off; off += P * zw[l] / 32; }      // sign bits of the pre-activations of z_1 .. z_5
     if (cudaMalloc(&s->act, off * sizeof(float)) != cudaSuccess) return tc_fail(s, "tensor-core path: cannot allocate the activation buffers");
     if (cudaMemset(s->act, 0, off * sizeof(float)) != cudaSuccess) return tc_fail(s, "cudaMemset failed");
@@ -510,11 +519,12 @@ int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
     auto tlo = [&](int l) { return s->act + s->t_off[l] + P * s->widths[l + 1]; };
     auto maskp = [&](int l) { return reinterpret_cast<uint32_t*>(s->act + s->mask_off[l]); };
     float* g0 = s->act + s->g0_off;
+    float* featp = s->act + s->feat_off;
     float* dkeep = s->act + s->dist_off;
-    cudaFuncSetAttribute(tc_enc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmTotal);
-    cudaFuncSetAttribute(tc_enc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmTotal);
-    cudaFuncSetAttribute(tc_enc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmTotal);
-    cudaFuncSetAttribute(tc_enc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmTotal);
+    cudaFuncSetAttribute(tc_enc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_sm_total<false>());
+    cudaFuncSetAttribute(tc_enc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_sm_total<true>());
+    cudaFuncSetAttribute(tc_enc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_sm_total<false>());
+    cudaFuncSetAttribute(tc_enc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, enc_sm_total<true>());
     const unsigned tiles32 = (unsigned)((a.B + kTileM - 1) / kTileM);
     const float* pose_cur = a.pose_in;
     for (int step = 0; step < a.steps; ++step) {
@@ -522,8 +532,9 @@ int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
         EncParams ep{};
         ep.pose = pose_cur; ep.encw = a.encw; ep.z0_hi = zhi(0); ep.z0_lo = zlo(0); ep.B = a.B; ep.z0_ld = zw[0];
         ep.normalise = a.normalise; ep.use_enc = cfg.use_enc; ep.enc_act = cfg.enc_act; ep.enc_beta = cfg.enc_beta;
-        if (esoft) tc_enc_kernel<true, false><<<tiles32, 256, kEncSmTotal, st>>>(ep);
-        else tc_enc_kernel<false, false><<<tiles32, 256, kEncSmTotal, st>>>(ep);
+        ep.feat_out = a.want_grad ? featp : nullptr;
+        if (esoft) tc_enc_kernel<true, false><<<tiles32, 256, enc_sm_total<false>(), st>>>(ep);
+        else tc_enc_kernel<false, false><<<tiles32, 256, enc_sm_total<false>(), st>>>(ep);
         if (tc_check(s, "tc_enc_kernel (forward) launch")) return 1;
         // ---- forward chain
         for (int l = 0; l < 6; ++l) {
@@ -568,8 +579,9 @@ int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
         rp.grad = last ? a.grad : nullptr;
         rp.pose_out = a.do_step ? a.pose_out : nullptr;
         if (last && a.do_step) { rp.n_peers = a.n_peers; for (int r = 0; r < a.n_peers; ++r) rp.peer_pose[r] = a.peer_pose[r]; }
-        if (esoft) tc_enc_kernel<true, true><<<tiles32, 256, kEncSmTotal, st>>>(rp);
-        else tc_enc_kernel<false, true><<<tiles32, 256, kEncSmTotal, st>>>(rp);
+        rp.feat = featp; rp.feat_out = nullptr; rp.pose = pose_cur;
+        if (esoft) tc_enc_kernel<true, true><<<tiles32, 256, enc_sm_total<true>(), st>>>(rp);
+        else tc_enc_kernel<false, true><<<tiles32, 256, enc_sm_total<true>(), st>>>(rp);
         if (tc_check(s, "tc_enc_kernel (reverse) launch")) return 1;
         if (launches) *launches += 7;
         pose_cur = a.pose_out;       // the next step starts from the projected poses
