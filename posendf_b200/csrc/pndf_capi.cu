@@ -45,7 +45,10 @@ int fail(const std::string& msg) {
 const int kAmassDims[6] = {256, 512, 1024, 512, 256, 64};
 const double kSmallTileCost = 0.40;      // time of an 8-pose tile relative to a 32-pose tile (measured)
 const long long kTcChunk = 131072;       // poses per pass of the tensor-core path (5.7 GB of activations)
-const long long kTcMinBatch = 6144;      // from this batch size on the DFNet GEMMs run on the tensor cores (pndf_tc.cu; measured crossover ~4 096)
+// From one pose more than a single round of 8-pose tiles covers (8 x SMs = 1 184) the DFNet GEMMs run on the tensor cores
+// (pndf_tc.cu).  Measured, forward + d(dist)/d(pose) + step, lrelu (tools/small_batch_bench.py): 1 024 poses 195 us (8-pose tiles) vs
+// 252 us; 1 536: 389 vs 270 us; 4 736: 459 (32-pose tiles) vs 301 us; 8 192: 917 vs 412 us.
+inline bool tc_batch(const pndf_handle* h, long long B);
 
 }  // namespace
 
@@ -104,6 +107,10 @@ struct pndf_handle {
     int tile_policy = 0;                 // 0: per launch from its batch size, 8 / 32 / 128: pinned (pndf_set_tile_policy); 128 = tensor-core path
     TcState* tc = nullptr;               // tensor-core DFNet path (pndf_tc.cu); nullptr if it could not be set up
 };
+
+namespace {
+inline bool tc_batch(const pndf_handle* h, long long B) { return B > 8LL * h->num_sms; }
+}  // namespace
 
 namespace {
 
@@ -340,7 +347,7 @@ bool use_tc(const pndf_handle* h, const KParams& p, int mode) {
         return false;
     if (const char* e = getenv("PNDF_TILE")) return atoi(e) == 128;
     if (h->tile_policy != 0) return h->tile_policy == 128;
-    return p.B >= kTcMinBatch;
+    return tc_batch(h, p.B);
 }
 
 int ensure_slot(pndf_handle* h, int slot) {
@@ -651,7 +658,7 @@ int pndf_project_host(pndf_handle* h, const float* pose_in_host, float* pose_out
     if (ensure_slot(h, 1) || ensure_slot(h, 2)) return 1;   // the two streams overlap: each needs its own per-CTA scratch
     // one tile size for all chunks, the one the whole batch would get: the result equals pndf_project on the same batch bit for bit
     const int saved_policy = h->tile_policy;
-    if (saved_policy == 0) h->tile_policy = (h->tc && B >= kTcMinBatch) ? 128 : (small_tile_for(h, B) ? 8 : 32);
+    if (saved_policy == 0) h->tile_policy = (h->tc && tc_batch(h, B)) ? 128 : (small_tile_for(h, B) ? 8 : 32);
     struct Restore { pndf_handle* h; int v; ~Restore() { h->tile_policy = v; } } restore{h, saved_policy};
     int which = 0;
     for (int64_t off = 0; off < B; off += chunk, which ^= 1) {
@@ -1176,7 +1183,7 @@ int pndf_set_tile_policy(pndf_handle* h, int tile) {
 }
 int pndf_tile_for_batch(pndf_handle* h, int64_t B, int* tile) {
     if (!h || !tile || B < 0) return fail("bad argument");
-    *tile = (h->tc && B >= kTcMinBatch) ? 128 : (small_tile_for(h, B) ? 8 : 32);
+    *tile = (h->tc && tc_batch(h, B)) ? 128 : (small_tile_for(h, B) ? 8 : 32);
     return 0;
 }
 

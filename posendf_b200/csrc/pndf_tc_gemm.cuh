@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     // tiled output (the next GEMM's A operand): this warp's 32 rows x 32 columns are ONE contiguous 4 KB block = one TMA
                     // box.  Row `lane` of the staging block, 16-byte chunk c at position c ^ (lane & 7): the 128-byte swizzle the tensor
                     // map undoes on the way out, and conflict-free for the warp's STS.128.
+#ifndef PNDF_TC_STAGED_STORE      // (staging read back with LDS.128 + 512-byte-per-instruction STG.128 measured the same: 2.17 vs 2.16 ms)
                     tma_store_wait_read();              // the previous store of this warp has finished reading the block
                     __syncwarp();
 #pragma unroll
@@ -308,6 +309,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         tma_store_2d(&maps.out[w], 0, c1, reinterpret_cast<const void*>(out_stage + (warp - 2) * kOutStage));
                         tma_store_commit();
                     }
+#else
+                    __syncwarp();                       // the previous block has been read out
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float* o = (w == 0) ? &o0[4 * c] : &o1[4 * c];
+                        st_shared_v4(stg + lane * 128 + ((c ^ (lane & 7)) << 4), o[0], o[1], o[2], o[3]);
+                    }
+                    __syncwarp();
+                    float* out = epi.out(w) + tiled_offset(m0 + quarter * 32, col0, epi.ld());
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {      // 4 rows x 128 bytes = 512 contiguous bytes per instruction
+                        const int r = i * 4 + (lane >> 3), c = lane & 7;
+                        float4 t;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                     : "r"(stg + r * 128 + ((c ^ (r & 7)) << 4)));
+                        *reinterpret_cast<float4*>(out + r * 32 + c * 4) = t;
+                    }
+#endif
                 }
             }
         }

@@ -10,10 +10,12 @@ act = sys.argv[1] if len(sys.argv) > 1 else "lrelu"
 eng = Engine(device=0, enc_act=act, df_act=act)
 eng.set_weights_flat(synth.flatten_params(synth.make_params(1)))
 out = {}
-for B in (10, 64, 320, 1024, 1184, 2368, 3552, 4736):
+sizes = [int(v) for v in os.environ.get("PNDF_SIZES", "10,64,320,1024,1184,2368,3552,4736").split(",")]
+tiles = os.environ.get("PNDF_TILES", "32,8,auto").split(",")      # add 128 for the tensor-core path
+for B in sizes:
     x0 = torch.from_numpy(synth.make_poses(3, B)).cuda().contiguous()
     row = {}
-    for tile in ("32", "8", "auto"):
+    for tile in tiles:
         if tile == "auto":
             os.environ.pop("PNDF_TILE", None)
         else:
