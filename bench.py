@@ -411,11 +411,13 @@ def main():
         tc = path_tile == 128
         tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0            # dense tf32 = half the measured dense bf16 rate
         tc_alg_tf = k_rate * FLOPS_PER_PROJECTION / 1e12                     # algorithmic (fp32-equivalent) flops of the step
+        traffic_tc, gemm_share = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic_tc.json")) as f:
-                traffic_tc = json.load(f).get("dram_bytes_per_step")
+                tj = json.load(f)
+            traffic_tc, gemm_share = tj.get("dram_bytes_per_step"), tj.get("gemm_share")
         except Exception:
-            traffic_tc = None
+            pass
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -434,8 +436,16 @@ def main():
                                 else f"fused fp32-FMA kernel, {path_tile}-pose tiles")},
             "roofline": ({"bound": "tensor", "achieved": 3.0 * tc_alg_tf, "peak": tf32_peak, "unit": "TFLOP/s",
                           "frac": 3.0 * tc_alg_tf / tf32_peak, "traffic": traffic_tc,
-                          "kernel": "tc_gemm_kernel (12 launches per step: 6 forward + 6 reverse DFNet layers, 87 % of the step)",
+                          "kernel": "tc_gemm_kernel: 12 of the 15 launches of a step (6 forward + 6 reverse DFNet layers)"
+                                    + (", %.0f %% of the step's device time in the ncu launch list (profiles/ncu_tc_path_r02.json)"
+                                       % (100.0 * gemm_share) if gemm_share else ""),
                           "kernel_ms": kernel_ms, "achieved_fp32_equivalent": tc_alg_tf,
+                          "gemm_kernels_only": ({"ms": kernel_ms * gemm_share, "achieved": 3.0 * tc_alg_tf / gemm_share,
+                                                 "frac": 3.0 * tc_alg_tf / gemm_share / tf32_peak,
+                                                 "note": "the step's CUDA-event time x the GEMM kernels' share of it in the ncu launch "
+                                                         "list; all algorithmic flops of the step are GEMM flops"}
+                                                if gemm_share else None),
+                          "frac_algorithmic_of_bf16_peak": tc_alg_tf / float(peaks.get("bf16_tflops", 1590.0)),
                           "peak_source": peak_src + ": dense bf16 %.1f TFLOP/s (burst) / 2 = dense tf32; `achieved` counts the tf32 MMA "
                                          "flops actually issued = 3 x the algorithmic flops (3xTF32 split: hi*hi + lo*hi + hi*lo); the "
                                          "denominator is the whole step (encoder / head kernels included)" % float(peaks.get("bf16_tflops", 1590.0)),

@@ -46,7 +46,7 @@ for r in data:
 json.dump({"what": "every kernel of ONE tensor-core projection step over 65 536 poses (lrelu), `ncu --set full --clock-control none`, "
                    "in launch order; times are serialised, cold-cache ncu replays",
            "sum_us": tot_us, "gemm_share": gemm_us / tot_us, "kernels": res}, open(out, "w"), indent=1)
-json.dump({"kernels": len(res), "dram_bytes_read_per_step": tot_rd, "dram_bytes_write_per_step": tot_wr,
+json.dump({"kernels": len(res), "gemm_share": gemm_us / tot_us, "step_us_under_ncu": tot_us, "dram_bytes_read_per_step": tot_rd, "dram_bytes_write_per_step": tot_wr,
            "dram_bytes_per_step": tot_rd + tot_wr, "step": "65 536 poses, 1 projection step on the tensor-core path (bench.py workload)",
            "note": "sum over the 15 launches of one step; the activations between the layer GEMMs (hi / lo planes, masks) are the "
                    "traffic -- algorithmic bytes of the step are 65 536 x 676",
