@@ -268,14 +268,17 @@ int pndf_knn_exact(int device, const float* query_dev, int64_t Q, const float* d
  *     variant 0 = scalar FFMA, 1 / 5 = packed FFMA2 (fma.rn.f32x2) with the pose scalar / the feature pair as the
  *     reused operand, 2-4 / 10-11 = probes used while tuning (operand traffic, legacy mma.sync).
  *   pndf_launch_count: number of kernel launches this handle has enqueued so far. */
-/* Tile size / arithmetic path of the forward / forward+reverse launches.  By default every launch picks it from ITS batch size:
- * the tensor-core path ("tile 128": DFNet GEMMs as 3xTF32 tcgen05 kernels on 128-pose tiles, pndf_tc.cu) for plain quaternion
- * batches of >= 6 144 poses, else the fused FFMA kernel with 32-pose tiles, or its 8-pose small-tile variant while the 32-pose
- * tiling cannot give every SM a tile (B <= ~2 400; 2.4x lower latency at the reference's real call sites, B = 10 in
- * experiments/sample_poses.py:96).  The paths differ in fp32 summation order / split arithmetic (same parity bars), so a caller that splits ONE batch over several launches or GPUs and wants bits identical to the unsplit
- * run pins the tile the whole batch would get: tile = pndf_tile_for_batch(h, B_total), pndf_set_tile_policy(h, tile), launches,
- * pndf_set_tile_policy(h, 0).  posendf_b200/dist.py and pndf_project_host do this.  PNDF_TILE=8|32 in the environment
- * overrides everything (tests, tuning). */
+/* Tile size / arithmetic engine of the forward / forward+reverse launches.  By default every launch picks it from ITS batch size:
+ *   B <= 8 x SMs (1 184 on a B200): the fused FFMA kernel's 8-pose small-tile variant (2.4x lower latency than 32-pose tiles at the
+ *     reference's real call sites, B = 10 in experiments/sample_poses.py:96);
+ *   larger plain quaternion batches: the tensor-core engine ("tile 128": DFNet GEMMs as 3xTF32 tcgen05 kernels on 128-pose
+ *     tiles, pndf_tc.cu);
+ *   axis-angle input, training exports, tangent launches: the fused FFMA kernel with 32-pose tiles (8-pose tiles while one round
+ *     of them covers the batch).
+ * The engines differ in fp32 summation order / split arithmetic (same parity bars), so a caller that splits ONE batch over several
+ * launches or GPUs and wants bits identical to the unsplit run pins the tile the whole batch would get:
+ * tile = pndf_tile_for_batch(h, B_total), pndf_set_tile_policy(h, tile), launches, pndf_set_tile_policy(h, 0).
+ * posendf_b200/dist.py and pndf_project_host do this.  PNDF_TILE=8|32|128 in the environment overrides everything (tests, tuning). */
 int pndf_set_tile_policy(pndf_handle* h, int tile);
 int pndf_tile_for_batch(pndf_handle* h, int64_t B, int* tile);
 
