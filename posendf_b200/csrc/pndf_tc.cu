@@ -25,6 +25,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <array>
+#include <map>
 #include <vector>
 
 #include "pndf_kernel.cuh"
@@ -405,6 +407,9 @@ struct TcState {
     float* act = nullptr;
     long long z_off[7], t_off[6], g0_off = 0, dist_off = 0, mask_off[7] = {0, 0, 0, 0, 0, 0, 0}, feat_off = 0, act_floats = 0;
     int num_sms = 148;
+    // tensor maps of the GEMM launches, keyed by (operand / output addresses, shape): a step repeats the same twelve launches, and
+    // six cuTensorMapEncodeTiled calls per launch are host time the 15-launch step of a small batch does not have
+    std::map<std::array<unsigned long long, 8>, pndf_tc::GemmMaps> maps;
     std::string err;
 };
 
@@ -470,6 +475,7 @@ static int ensure_act(TcState* s, long long B) {
     if (P <= s->cap) return 0;
     cudaFree(s->act);
     s->act = nullptr;
+    s->maps.clear();
     long long off = 0;
     const int zw[7] = {s->kpad[0], 256, 512, 1024, 512, 256, 64};
     for (int l = 0; l < 7; ++l) { s->z_off[l] = off; off += 2 * P * zw[l]; }
@@ -490,12 +496,23 @@ template <int NT, class Epi>
 static int launch_gemm(TcState* s, const float* a_hi, const float* a_lo, long long P, int K, const float* b_hi, const float* b_lo, int N,
                        const Epi& epi, cudaStream_t st) {
     using namespace pndf_tc;
-    GemmMaps maps;
-    if (!make_map(&maps.a_hi, a_hi, P, K, pndf_tc::kTM) || !make_map(&maps.a_lo, a_lo, P, K, pndf_tc::kTM) || !make_map(&maps.b_hi, b_hi, N, K, NT) ||
-        !make_map(&maps.b_lo, b_lo, N, K, NT))
-        return tc_fail(s, "cuTensorMapEncodeTiled failed");
-    for (int w = 0; w < Epi::kOutputs; ++w)
-        if (!make_out_map(&maps.out[w], epi.out_host(w), P, epi.ldo)) return tc_fail(s, "cuTensorMapEncodeTiled failed (output)");
+    const std::array<unsigned long long, 8> key = {(unsigned long long)(uintptr_t)a_hi, (unsigned long long)(uintptr_t)a_lo,
+                                                   (unsigned long long)(uintptr_t)b_hi, (unsigned long long)(uintptr_t)epi.out_host(0),
+                                                   (unsigned long long)(uintptr_t)epi.out_host(Epi::kOutputs - 1), (unsigned long long)P,
+                                                   (unsigned long long)K, ((unsigned long long)N << 32) | (unsigned)NT};
+    auto it = s->maps.find(key);
+    if (it == s->maps.end()) {
+        GemmMaps m;
+        if (!make_map(&m.a_hi, a_hi, P, K, pndf_tc::kTM) || !make_map(&m.a_lo, a_lo, P, K, pndf_tc::kTM) || !make_map(&m.b_hi, b_hi, N, K, NT) ||
+            !make_map(&m.b_lo, b_lo, N, K, NT))
+            return tc_fail(s, "cuTensorMapEncodeTiled failed");
+        for (int w = 0; w < Epi::kOutputs; ++w)
+            if (!make_out_map(&m.out[w], epi.out_host(w), P, epi.ldo)) return tc_fail(s, "cuTensorMapEncodeTiled failed (output)");
+        if (Epi::kOutputs == 1) m.out[1] = m.out[0];
+        if (s->maps.size() > 256) s->maps.clear();      // batch sizes come and go; a map is cheap to rebuild
+        it = s->maps.emplace(key, m).first;
+    }
+    const GemmMaps& maps = it->second;
     auto kern = tc_gemm_kernel<NT, Epi>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pndf_tc::smem_bytes<NT>()) != cudaSuccess)
         return tc_fail(s, "cudaFuncSetAttribute failed");

@@ -1,0 +1,18 @@
+"""compute-sanitizer driver for the tensor-core engine (tile policy 128 forced): forward, forward + gradient, 2-step projection on a
+ragged batch, lrelu and softplus.  tools/sanitize_tc.sh runs it under memcheck, racecheck and synccheck."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["PNDF_TILE"] = "128"
+import torch
+from posendf_b200 import synth
+from posendf_b200.engine import Engine
+for act in ("lrelu", "softplus"):
+    eng = Engine(device=0, enc_act=act, df_act=act)
+    eng.set_weights_flat(synth.flatten_params(synth.make_params(1)))
+    B = 128 * 3 + 37
+    x = torch.from_numpy(synth.make_poses(3, B)).cuda().contiguous()
+    d = eng.forward(x); d2, g = eng.forward_grad(x)
+    y = x.clone(); eng.project_(y, steps=2)
+    torch.cuda.synchronize()
+    print(act, float(d.mean()), float((d - d2).abs().max()), float(g.abs().mean()), float((y - x).abs().max()), eng.launch_count())
+print("done")
