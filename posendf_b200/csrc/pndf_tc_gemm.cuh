@@ -28,7 +28,10 @@ namespace pndf_tc {
 constexpr int kTM = 128;                 // rows (poses) per tile = TMEM lanes
 constexpr int kKB = 32;                  // K per stage = one 128-byte swizzle row of tf32
 constexpr int kStages = 3;
-constexpr int kChunkK = 128;             // K depth per accumulator pair
+#ifndef PNDF_TC_CHUNK_K
+#define PNDF_TC_CHUNK_K 128
+#endif
+constexpr int kChunkK = PNDF_TC_CHUNK_K;  // K depth per accumulator pair
 constexpr int kThreads = 320;            // warp 0 TMA, warp 1 MMA, warps 2-9 drain / epilogue
 constexpr int kDrainWarps = 8;
 
@@ -79,6 +82,43 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster run ONE M = 256 MMA stream issued by the leader (cluster rank 0);
+// each CTA feeds its own 128 rows of A and its half of the B operand from its own shared memory
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {      // shared::cta address -> shared::cluster address in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on a barrier of the pair's leader
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in BOTH CTAs of the pair once all prior MMAs of this thread have retired
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
 // 256-bit global store / load (sm_100: STG.256 / LDG.256), 32-byte aligned
 __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
     asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
@@ -125,10 +165,15 @@ __host__ __device__ constexpr int stage_bytes() { return 2 * kTM * 128 + 2 * NT 
 constexpr int kOutStage = 32 * 128;      // per drain warp: one 32-row x 32-column output block, 128-byte swizzled, the source of a TMA store
 template <int NT>
 __host__ __device__ constexpr int smem_bytes() { return kStages * stage_bytes<NT>() + kDrainWarps * kOutStage + 1024 + 256; }
+// CTA pair: per stage and CTA A_hi, A_lo (its 128 rows), Bw = this CTA's half of [B_hi; B_lo] (rank 0: B_hi, rank 1: B_lo) and
+// Bx = its half of B_hi for the cross-term MMA (rank 0: rows [0, 64), rank 1: rows [64, 128))
+__host__ __device__ constexpr int pair_stage_bytes() { return 2 * kTM * 128 + 128 * 128 + 64 * 128; }
+__host__ __device__ constexpr int pair_smem_bytes() { return kStages * pair_stage_bytes() + kDrainWarps * kOutStage + 1024 + 256; }
 
 struct GemmMaps {
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     CUtensorMap out[2];      // the output arrays (tiled layout), box = 32 rows x 32 columns (one drain warp's block)
+    CUtensorMap b_x;         // CTA-pair kernels only: B_hi with a 64-row box
 };
 
 // Epilogue functor interface:
@@ -146,12 +191,22 @@ struct GemmMaps {
 // sums live in the drain warps' registers, so the TMEM accumulator pairs are free as soon as a tile's last chunk is drained: the
 // MMA warp starts the next tile while the drain warps are still busy with the previous tile's epilogue (activation, hi / lo split,
 // stores).
-template <int NT, class Epilogue>
+// PAIR = true (NT = 128 only, launched as clusters of 2 CTAs): the pair owns 256 x 128 output tiles; the leader issues
+// cta_group::2 MMAs -- A_hi x [B_hi; B_lo] as M = 256, N = 256 with B_hi in the leader's and B_lo in the peer's shared memory, and
+// A_lo x B_hi as M = 256, N = 128 with each CTA holding 64 rows of B_hi -- so every CTA's shared memory feeds 14 KB per 8-deep K
+// slice instead of 20 KB; accumulators, drain and epilogue stay per CTA (its 128 rows).
+template <int NT, class Epilogue, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmMaps maps, int K, int m_tiles, int n_tiles,
                                                               Epilogue epi) {
+    static_assert(!PAIR || NT == 128, "CTA pairs: 128-column tiles only");
+    constexpr int kStageBytes = PAIR ? pair_stage_bytes() : stage_bytes<NT>();
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    // work list: single CTAs walk (m tile, n tile); pairs walk (pair of m tiles, n tile) and each CTA takes the m tile of its rank
+    const int walker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, walkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto m_tile_of = [&](int tile) { return PAIR ? (tile / n_tiles) * 2 + (int)rank : tile / n_tiles; };
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* out_stage = smem + kStages * stage_bytes<NT>();       // [kDrainWarps][kOutStage], 1024-byte aligned blocks
+    uint8_t* out_stage = smem + kStages * kStageBytes;             // [kDrainWarps][kOutStage], 1024-byte aligned blocks
     uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kDrainWarps * kOutStage);
     uint64_t* full = bars;                   // [kStages]
     uint64_t* empty = bars + kStages;        // [kStages]
@@ -162,19 +217,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const int nks = K / kKB;
     constexpr int kStagesPerChunk = kChunkK / kKB;
     const int nchunks = (nks + kStagesPerChunk - 1) / kStagesPerChunk;
-    const int ntiles = m_tiles * n_tiles;
+    const int ntiles = (PAIR ? m_tiles / 2 : m_tiles) * n_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int p = 0; p < 2; ++p) { mbar_init(&acc_full[p], 1); mbar_init(&acc_empty[p], kDrainWarps); }
+        // (pair: the leader's acc_empty collects the drain warps of both CTAs)
+        for (int p = 0; p < 2; ++p) { mbar_init(&acc_full[p], 1); mbar_init(&acc_empty[p], PAIR ? 2 * kDrainWarps : kDrainWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(4 * NT < 32 ? 32 : 4 * NT));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (PAIR) {      // warp 0 of both CTAs, collectively
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(4 * NT));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(4 * NT < 32 ? 32 : 4 * NT));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();      // pair: the peer's barriers exist before anything is signalled on them
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = *tmem_slot;
 
@@ -182,25 +243,33 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t it = 0;      // running stage counter over all tiles of this CTA
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * NT;
+            for (int tile = walker; tile < ntiles; tile += walkers) {
+                const int mt = m_tile_of(tile), nt = tile % n_tiles;
                 for (int ks = 0; ks < nks; ++ks, ++it) {
                     const uint32_t s = it % kStages;
                     mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);      // fresh barrier: parity 1 passes
-                    uint8_t* st = smem + s * stage_bytes<NT>();
-#ifdef PNDF_TC_EXP_HALF_FEED      // bottleneck experiment (tools/tc_gemm.sh): only the hi operands travel, the MMAs run on stale lo tiles
-                    mbar_expect_tx(&full[s], stage_bytes<NT>() / 2);
-                    {
-                        const int ra = ((tile / n_tiles) * nks + ks) * kTM, rb = ((tile % n_tiles) * nks + ks) * NT;
-                        tma_load_2d(st, &maps.a_hi, 0, ra, &full[s]);
-                        tma_load_2d(st + 2 * kTM * 128, &maps.b_hi, 0, rb, &full[s]);
-                        continue;
-                    }
-#endif
-                    mbar_expect_tx(&full[s], stage_bytes<NT>());
+                    uint8_t* st = smem + s * kStageBytes;
                     // operands live in TILED layout: [row tile][K block][rows of the tile][32 floats] -- every TMA box (rows x 128 bytes) is
                     // one contiguous 16 KB (8 KB) block of memory instead of 128 row segments 2-4 KB apart
-                    const int ra = ((tile / n_tiles) * nks + ks) * kTM, rb = ((tile % n_tiles) * nks + ks) * NT;
+                    const int ra = (mt * nks + ks) * kTM, rb = (nt * nks + ks) * NT;
+                    if (PAIR) {
+                        // every byte of the pair's stage is counted on the LEADER's full barrier (the MMA issuer waits there)
+                        const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
+                        if (rank == 0) mbar_expect_tx(&full[s], 2 * pair_stage_bytes());
+                        const uint32_t d = smem_u32(st);
+                        tma_load_2d_pair(d, &maps.a_hi, 0, ra, bar);
+                        tma_load_2d_pair(d + kTM * 128, &maps.a_lo, 0, ra, bar);
+                        tma_load_2d_pair(d + 2 * kTM * 128, rank == 0 ? &maps.b_hi : &maps.b_lo, 0, rb, bar);
+                        tma_load_2d_pair(d + 2 * kTM * 128 + 128 * 128, &maps.b_x, 0, rb + 64 * (int)rank, bar);
+                        continue;
+                    }
+#ifdef PNDF_TC_EXP_HALF_FEED      // bottleneck experiment (tools/tc_gemm.sh): only the hi operands travel, the MMAs run on stale lo tiles
+                    mbar_expect_tx(&full[s], stage_bytes<NT>() / 2);
+                    tma_load_2d(st, &maps.a_hi, 0, ra, &full[s]);
+                    tma_load_2d(st + 2 * kTM * 128, &maps.b_hi, 0, rb, &full[s]);
+                    continue;
+#endif
+                    mbar_expect_tx(&full[s], stage_bytes<NT>());
                     tma_load_2d(st, &maps.a_hi, 0, ra, &full[s]);
                     tma_load_2d(st + kTM * 128, &maps.a_lo, 0, ra, &full[s]);
                     tma_load_2d(st + 2 * kTM * 128, &maps.b_hi, 0, rb, &full[s]);
@@ -210,20 +279,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            // D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * NT >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+        if (lane == 0 && rank == 0) {
+            // D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24 (pair: M = 256 over the two CTAs)
+            constexpr uint32_t kM = PAIR ? 2 * kTM : kTM;
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * NT >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
             uint32_t it = 0, cc = 0;      // running stage / chunk counters
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int tile = walker; tile < ntiles; tile += walkers) {
                 for (int ks = 0; ks < nks; ++ks, ++it) {
                     const uint32_t s = it % kStages, p = cc & 1;
                     const bool chunk_start = (ks % kStagesPerChunk) == 0;
                     if (chunk_start) mbar_wait(&acc_empty[p], ((cc >> 1) & 1) ^ 1);      // the drain of chunk cc-2 has emptied pair p
                     mbar_wait(&full[s], (it / kStages) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint32_t st = smem_u32(smem + s * stage_bytes<NT>());
-                    const uint32_t a_hi = st, a_lo = st + kTM * 128, b_hi = st + 2 * kTM * 128, b_lo = b_hi + NT * 128;
+                    const uint32_t st = smem_u32(smem + s * kStageBytes);
+                    const uint32_t a_hi = st, a_lo = st + kTM * 128, b_hi = st + 2 * kTM * 128, b_x = b_hi + 128 * 128;
                     const uint32_t acc_hh = tmem + (uint32_t)(p * 2 * NT), acc_x = acc_hh + NT;
 #pragma unroll
                     for (int k = 0; k < kKB / 8; ++k) {
@@ -231,12 +301,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                         // B_hi and B_lo are adjacent in the stage and acc_x follows acc_hh in TMEM: ONE N = 2 NT instruction computes
                         // A_hi B_hi -> acc_hh and A_hi B_lo -> acc_x and fetches A_hi once (the SS-mode operand fetch, about 64 B/clk
                         // for tf32, is what paces these MMAs: 24 KB -> 20 KB per 8-deep K slice, -10 % GEMM time)
-                        mma_tf32(acc_hh, make_desc(a_hi + k * 32), make_desc(b_hi + k * 32), idesc2, first);
-                        mma_tf32(acc_x, make_desc(a_lo + k * 32), make_desc(b_hi + k * 32), idesc, 1u);
+                        if (PAIR) {
+                            mma_tf32_pair(acc_hh, make_desc(a_hi + k * 32), make_desc(b_hi + k * 32), idesc2, first);
+                            mma_tf32_pair(acc_x, make_desc(a_lo + k * 32), make_desc(b_x + k * 32), idesc, 1u);
+                        } else {
+                            mma_tf32(acc_hh, make_desc(a_hi + k * 32), make_desc(b_hi + k * 32), idesc2, first);
+                            mma_tf32(acc_x, make_desc(a_lo + k * 32), make_desc(b_hi + k * 32), idesc, 1u);
+                        }
                     }
-                    mma_commit(&empty[s]);                                               // stage s may be refilled once these MMAs retire
+                    if (PAIR) mma_commit_pair(&empty[s]); else mma_commit(&empty[s]);      // stage s may be refilled once these MMAs retire
                     if ((ks % kStagesPerChunk) == kStagesPerChunk - 1 || ks == nks - 1) {
-                        mma_commit(&acc_full[p]);
+                        if (PAIR) mma_commit_pair(&acc_full[p]); else mma_commit(&acc_full[p]);
                         ++cc;
                     }
                 }
@@ -252,8 +327,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         constexpr int NH = NT / 2;
         const uint32_t stg = smem_u32(out_stage + (warp - 2) * kOutStage);
         uint32_t cc = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int m0 = (tile / n_tiles) * kTM, n0 = (tile % n_tiles) * NT;
+        const uint32_t acc_empty_leader[2] = {PAIR ? mapa_u32(smem_u32(&acc_empty[0]), 0) : 0u, PAIR ? mapa_u32(smem_u32(&acc_empty[1]), 0) : 0u};
+        for (int tile = walker; tile < ntiles; tile += walkers) {
+            const int m0 = m_tile_of(tile) * kTM, n0 = (tile % n_tiles) * NT;
             const int row = m0 + quarter * 32 + lane;
             float run[NH];
 #pragma unroll
@@ -276,7 +352,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #endif
                 asm volatile("tcgen05.fence::before_thread_sync;");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&acc_empty[p]);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_cluster(acc_empty_leader[p]); else mbar_arrive(&acc_empty[p]);
+                }
             }
             // epilogue of this tile (the MMA warp is already on the next one)
 #ifdef PNDF_TC_EXP_NO_EPI       // bottleneck experiment: nothing is computed or stored after the drain
@@ -333,10 +411,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // this warp's last stores have landed before the CTA retires
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();      // pair: no CTA retires while the other may still signal its barriers
     if (warp == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(4 * NT < 32 ? 32 : 4 * NT));
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(4 * NT));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(4 * NT < 32 ? 32 : 4 * NT));
     }
 }
 
@@ -366,6 +445,21 @@ inline bool make_map(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// launch of a CTA-pair kernel: clusters of 2 CTAs (two SMs of one TPC), an even grid
+template <class Kern, class... Args>
+inline cudaError_t launch_pair(Kern kern, int grid, int smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(grid & ~1));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 // output map of a GEMM: the tiled [rows][ld] array, one drain warp's 32 x 32 block per store
 inline bool make_out_map(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t ld) { return make_map(tm, base, rows, ld, 32); }
 

@@ -122,6 +122,31 @@ static void run_case(int M, int N, int K) {
         printf("   two-output epilogue (bias + lrelu + hi/lo): %.3f ms  %.1f TFLOP/s fp32-equivalent\n", ms2, 2.0 * M * N * K / ms2 / 1e9);
         cudaFree(dHi); cudaFree(dLo); cudaFree(dBias);
     }
+    if (NT == 128 && M % 256 == 0) {      // the same GEMM on CTA pairs (cta_group::2)
+        GemmMaps mp = maps;
+        if (!make_map(&mp.b_x, dBhi, N, K, 64)) { printf("tensor map creation failed\n"); exit(1); }
+        auto kp = tc_gemm_kernel<128, StoreEpi, true>;
+        CK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem_bytes()));
+        CK(cudaMemset(dD, 0, (size_t)M * N * 4));
+        const int gp = std::min((m_tiles / 2) * n_tiles * 2, 148);
+        CK(launch_pair(kp, gp, pair_smem_bytes(), 0, mp, K, m_tiles, n_tiles, epi));
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+        double ep = 0;
+        for (int m = 0; m < M; m += std::max(1, M / 97))
+            for (int n = 0; n < N; ++n) {
+                double sd = 0;
+                for (int k = 0; k < K; ++k) sd += (double)A[(size_t)m * K + k] * (double)B[(size_t)n * K + k];
+                ep = std::max(ep, std::fabs((double)D[tiled_offset(m, n, N, kTM)] - sd));
+            }
+        for (int i = 0; i < 3; ++i) launch_pair(kp, gp, pair_smem_bytes(), 0, mp, K, m_tiles, n_tiles, epi);
+        cudaEventRecord(e0);
+        for (int i = 0; i < reps; ++i) launch_pair(kp, gp, pair_smem_bytes(), 0, mp, K, m_tiles, n_tiles, epi);
+        cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+        float msp; cudaEventElapsedTime(&msp, e0, e1); msp /= reps;
+        printf("   CTA pairs (cta_group::2, 256 x 128 tiles): max err %.3e (= %.2e rel)   %.3f ms  %.1f TFLOP/s fp32-equivalent\n", ep, ep / scale, msp,
+               flop / msp / 1e9);
+    }
     printf("M %6d N %5d K %5d NT %3d: max err %.3e of scale %.3f (= %.2e rel; fp32 FMA chain %.2e)   %.3f ms  %.1f TFLOP/s fp32-equivalent (%.0f tf32 TFLOP/s)\n",
            M, N, K, NT, emax, scale, emax / scale, e32 / scale, ms, flop / ms / 1e9, 3 * flop / ms / 1e9);
     cudaFree(dAhi); cudaFree(dAlo); cudaFree(dBhi); cudaFree(dBlo); cudaFree(dD);
