@@ -194,7 +194,9 @@ struct GemmMaps {
 // PAIR = true (NT = 128 only, launched as clusters of 2 CTAs): the pair owns 256 x 128 output tiles; the leader issues
 // cta_group::2 MMAs -- A_hi x [B_hi; B_lo] as M = 256, N = 256 with B_hi in the leader's and B_lo in the peer's shared memory, and
 // A_lo x B_hi as M = 256, N = 128 with each CTA holding 64 rows of B_hi -- so every CTA's shared memory feeds 14 KB per 8-deep K
-// slice instead of 20 KB; accumulators, drain and epilogue stay per CTA (its 128 rows).
+// slice instead of 20 KB; accumulators, drain and epilogue stay per CTA (its 128 rows).  MEASURED (tools/tc_gemm_test.cu,
+// profiles/tc_experiments_r02.txt): bit-identical results, 0.299 vs 0.292 ms on the 65 536 x 1 024 x 512 GEMM -- no gain, so the
+// product launches PAIR = false; the variant stays as the tested starting point for 256 x 256 pair tiles.
 template <int NT, class Epilogue, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ GemmMaps maps, int K, int m_tiles, int n_tiles,
                                                               Epilogue epi) {
@@ -299,8 +301,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     for (int k = 0; k < kKB / 8; ++k) {
                         const uint32_t first = (chunk_start && k == 0) ? 0u : 1u;
                         // B_hi and B_lo are adjacent in the stage and acc_x follows acc_hh in TMEM: ONE N = 2 NT instruction computes
-                        // A_hi B_hi -> acc_hh and A_hi B_lo -> acc_x and fetches A_hi once (the SS-mode operand fetch, about 64 B/clk
-                        // for tf32, is what paces these MMAs: 24 KB -> 20 KB per 8-deep K slice, -10 % GEMM time)
+                        // A_hi B_hi -> acc_hh and A_hi B_lo -> acc_x (two instructions per 8-deep K slice instead of three, A_hi
+                        // fetched once: -10 % GEMM time).  The CTA-pair variant cuts the per-CTA operand fetch further (20 -> 14 KB
+                        // per slice) and measured the same time as this one: operand fetch is not what paces the stream.
                         if (PAIR) {
                             mma_tf32_pair(acc_hh, make_desc(a_hi + k * 32), make_desc(b_hi + k * 32), idesc2, first);
                             mma_tf32_pair(acc_x, make_desc(a_lo + k * 32), make_desc(b_x + k * 32), idesc, 1u);
