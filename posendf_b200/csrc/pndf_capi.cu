@@ -55,6 +55,7 @@ inline bool tc_batch(const pndf_handle* h, long long B);
 struct pndf_handle {
     pndf_config cfg;
     int num_sms = 0;
+    bool no_tc = false;           // set while a caller runs launch chains side by side (the tensor-core engine has ONE set of buffers)
     bool have_weights = false;
     float* d_wstream = nullptr;   // slab stream
     size_t wstream_floats = 0;
@@ -341,13 +342,24 @@ bool use_small_tile(const pndf_handle* h, const KParams& p, int mode) {
 // Large batches of plain quaternion poses (forward, forward + gradient, projection steps) take the tensor-core path: the DFNet
 // GEMMs as 3xTF32 tcgen05 kernels, ~2x the FFMA kernel.  Everything else (axis-angle prior / denoise loop, training
 // exports, debug dump, small batches) stays on the fused FFMA kernel.
-bool use_tc(const pndf_handle* h, const KParams& p, int mode) {
-    if (!h->tc || mode == 2 || p.dbg != nullptr || p.act_masks != nullptr || p.tan_in != nullptr || p.input_kind != IN_QUAT ||
-        p.dn.pending != 0 || (mode == 1 && p.steps > 1 && p.pose_out == nullptr))
-        return false;
+// the engine a plain launch over B poses gets (environment override, pinned policy, batch size)
+bool tc_for_batch(const pndf_handle* h, long long B) {
+    if (!h->tc) return false;
     if (const char* e = getenv("PNDF_TILE")) return atoi(e) == 128;
     if (h->tile_policy != 0) return h->tile_policy == 128;
-    return tc_batch(h, p.B);
+    return tc_batch(h, B);
+}
+// axis-angle input = the prior mode (one evaluation + VJP, optionally with a denoise loop's pending Adam update in the prologue): on
+// the tensor-core engine as one pass (sequence bookkeeping does not survive the chunking of very large batches)
+bool tc_prior_ok(const KParams& p, int mode) {
+    return mode == 1 && p.steps == 1 && !p.do_step && p.pose_out == nullptr && p.n_peers == 0 && p.B <= kTcChunk;
+}
+bool use_tc(const pndf_handle* h, const KParams& p, int mode) {
+    if (!h->tc || h->no_tc || mode == 2 || p.dbg != nullptr || p.act_masks != nullptr || p.tan_in != nullptr ||
+        (mode == 1 && p.steps > 1 && p.pose_out == nullptr))
+        return false;
+    if ((p.input_kind != IN_QUAT || p.dn.pending != 0) && !tc_prior_ok(p, mode)) return false;
+    return tc_for_batch(h, p.B);
 }
 
 int ensure_slot(pndf_handle* h, int slot) {
@@ -385,7 +397,17 @@ int launch(pndf_handle* h, KParams& p, int mode, cudaStream_t st, int slot = 0) 
         a.encw = p.encw; a.w6 = p.w6; a.n_peers = p.n_peers;
         for (int l = 0; l < 7; ++l) a.bias[l] = p.bias[l];
         for (int r = 0; r < p.n_peers; ++r) { a.peer_pose[r] = p.peer_pose[r]; a.peer_dist[r] = p.peer_dist[r]; }
+        a.input_kind = p.input_kind;
+        a.dn = (p.dn.pending != 0) ? &p.dn : nullptr;
         if (!h->in_capture && order_after_weights(h, st)) return 1;
+        if (p.input_kind != IN_QUAT) {      // prior mode: one pass (use_tc has checked B <= kTcChunk)
+            if (tc_run(h->tc, a, st, &h->launches)) return fail(std::string("tensor-core path: ") + tc_last_error(h->tc));
+            if (h->in_capture) return 0;
+            CUDA_OK(cudaEventRecord(h->use_event, st));
+            h->use_stream = st;
+            h->used = true;
+            return 0;
+        }
         // the activations of the whole DFNet chain live in HBM between the layer kernels (43.5 KB per pose): bound them by walking
         // very large batches in chunks of kTcChunk poses (every pose is independent; all steps of a chunk run before the next chunk)
         for (long long off = 0; off < p.B; off += kTcChunk) {
@@ -733,7 +755,13 @@ int pndf_denoise_prior(pndf_handle* h, float* aa_dev, int64_t S, int64_t T, int 
     // side (second internal stream = a parallel branch of the graph, its own per-CTA scratch slot): when the persistent CTAs of
     // one group's launch run out of tiles, the other group's next launch takes over their SMs -- without it 1 200 tiles on 148
     // SMs (config C4) leave the ninth round 90 % empty in every one of the 100 steps.
-    const int G = (S >= 2 && h->dn_stream2 != nullptr) ? 2 : 1;
+    // On the tensor-core engine (one set of activation buffers per handle) the loop is ONE chain over all sequences; its buffers
+    // are reserved before the capture starts.
+    const bool on_tc = tc_for_batch(h, B) && B <= kTcChunk;
+    if (on_tc && tc_reserve(h->tc, B)) return fail(std::string("tensor-core path: ") + tc_last_error(h->tc));
+    const int G = (!on_tc && S >= 2 && h->dn_stream2 != nullptr) ? 2 : 1;
+    struct NoTc { pndf_handle* h; bool v; ~NoTc() { h->no_tc = v; } } no_tc_guard{h, h->no_tc};
+    h->no_tc = !on_tc;            // two sequence groups = two concurrent chains: fused engine only
     auto enqueue = [&](cudaStream_t s0) -> int {
         if (cudaMemsetAsync(m, 0, (size_t)B * 63 * sizeof(float), s0) != cudaSuccess) return fail("cudaMemsetAsync failed");
         if (cudaMemsetAsync(v, 0, (size_t)B * 63 * sizeof(float), s0) != cudaSuccess) return fail("cudaMemsetAsync failed");

@@ -198,6 +198,10 @@ struct EncParams {
     long long B;
     int z0_ld, normalise, use_enc, enc_act, do_step, renorm, n_peers;
     float enc_beta;
+    // prior mode (experiments/motion_denoise.py:81-83): `pose` is [B][63] axis-angle, `grad` its [B][63] VJP; the forward kernel applies
+    // the pending Adam update of a denoise loop first (same prologue as the fused kernel's, pndf_kernel.cuh)
+    int input_kind;
+    DenoiseFuse dn;
 };
 // shared-memory layout: the forward kernel needs no gradient buffer (5 CTAs per SM), the reverse kernel no encoder recomputation
 // (3 CTAs per SM): both are latency-bound prologue -> tree walk -> epilogue pipelines, occupancy is what overlaps them
@@ -224,7 +228,61 @@ __global__ void __launch_bounds__(256) tc_enc_kernel(const EncParams p) {
     enc.l = lane & 7; enc.base = lane & 24; enc.m = warp * 4 + (lane >> 3);
     const float apar = ESOFT ? p.enc_beta : ((p.enc_act == ACT_RELU) ? 0.0f : 0.01f);
 
-    for (int idx = tid; idx < kTileM * 84; idx += 256) qs[idx] = (idx < nvalid * 84) ? __ldg(p.pose + pose0 * 84 + idx) : 0.0f;      // raw x, scaled in place
+    const bool aa_in = (p.input_kind != IN_QUAT);
+    if (!aa_in) {
+        for (int idx = tid; idx < kTileM * 84; idx += 256) qs[idx] = (idx < nvalid * 84) ? __ldg(p.pose + pose0 * 84 + idx) : 0.0f;      // raw x, scaled in place
+    } else {
+        __shared__ float s_red[8];
+        __shared__ float s_scale[kTileM + 1];
+        const float* src = p.pose + pose0 * 63;
+        const bool dn = !REVERSE && (p.dn.pending != 0);
+        if (dn) {
+            // per-sequence loss scale of the PREVIOUS step for every sequence that has a frame in this tile:
+            // c = mean_t dist_prev[s][t] (same summation order as seq_adam_kernel), scale = weight * 2 c / T
+            const int T = p.dn.T;
+            const long long s_lo = pose0 / T, s_hi = (pose0 + nvalid - 1) / T;
+            for (long long sq = s_lo; sq <= s_hi; ++sq) {
+                const float* dp = p.dn.dist_prev + sq * T;
+                float acc = 0.0f;
+                for (int t = tid; t < T; t += 256) acc += dp[t];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) s_red[warp] = acc;
+                __syncthreads();
+                if (tid == 0) {
+                    float tot = 0.0f;
+                    for (int w = 0; w < 8; ++w) tot += s_red[w];
+                    const float cmean = tot / (float)T;
+                    s_scale[sq - s_lo] = p.dn.ap.weight * 2.0f * cmean / (float)T;
+                    if (p.dn.loss_out != nullptr && sq * T >= pose0) p.dn.loss_out[sq] = p.dn.ap.weight * cmean * cmean;
+                }
+                __syncthreads();
+            }
+        }
+        for (int idx = tid; idx < kTileM * 21; idx += 256) {
+            const int m = idx / 21, j = idx - m * 21;
+            float a[3] = {0.f, 0.f, 0.f}, q[4];
+            if (m < nvalid) {
+                if (dn) {
+                    const long long e0 = (pose0 * 21 + idx) * 3;
+                    const float scale = s_scale[(pose0 + m) / p.dn.T - pose0 / p.dn.T];
+#pragma unroll
+                    for (int k3 = 0; k3 < 3; ++k3) {
+                        float av = p.dn.pose_rw[e0 + k3], mv = p.dn.m[e0 + k3], vv = p.dn.v[e0 + k3];
+                        dn_adam_update(av, mv, vv, p.dn.graw[e0 + k3], scale, p.dn.ap);
+                        p.dn.pose_rw[e0 + k3] = av; p.dn.m[e0 + k3] = mv; p.dn.v[e0 + k3] = vv;
+                        a[k3] = av;
+                    }
+                } else {
+                    // plain loads: in a denoise step the forward kernel of this step has just rewritten these values
+                    a[0] = src[idx * 3]; a[1] = src[idx * 3 + 1]; a[2] = src[idx * 3 + 2];
+                }
+            }
+            aa_to_quat(a, q);
+#pragma unroll
+            for (int cpt = 0; cpt < 4; ++cpt) qs[m * kXS + j * 4 + cpt] = (m < nvalid) ? q[cpt] : 0.0f;
+        }
+    }
     if (p.use_enc)
         for (int i = tid; i < kEncFloats; i += 256) encw[i] = __ldg(p.encw + i);
     if (REVERSE) {      // dd/dz0 and the features of this tile, pose-major in HBM -> [feature][pose]
@@ -324,6 +382,21 @@ __global__ void __launch_bounds__(256) tc_enc_kernel(const EncParams p) {
         }
     }
     __syncthreads();
+    if (aa_in) {      // prior mode: the VJP through aa -> quat, no step
+        if (p.grad != nullptr) {
+            const float* src = p.pose + pose0 * 63;
+            float* dst = p.grad + pose0 * 63;
+            for (int idx = tid; idx < nvalid * 21; idx += 256) {
+                const int m = idx / 21, j = idx - m * 21;
+                const float a[3] = {src[idx * 3], src[idx * 3 + 1], src[idx * 3 + 2]};
+                const float qb[4] = {Y[swz(128 + j * 4, m)], Y[swz(128 + j * 4 + 1, m)], Y[swz(128 + j * 4 + 2, m)], Y[swz(128 + j * 4 + 3, m)]};
+                float ab[3];
+                aa_to_quat_vjp(a, qb, ab);
+                dst[idx * 3] = ab[0]; dst[idx * 3 + 1] = ab[1]; dst[idx * 3 + 2] = ab[2];
+            }
+        }
+        return;
+    }
     for (int idx = tid; idx < nvalid * 84; idx += 256) {
         const int m = idx / 84, e = idx - m * 84;
         if (p.grad != nullptr) p.grad[pose0 * 84 + idx] = Y[swz(128 + e, m)];
@@ -470,6 +543,8 @@ int tc_set_weights(TcState* s, const float* flat_dev, cudaStream_t st) {
     return tc_check(s, "tc_split_weights_kernel launch");
 }
 
+static int ensure_act(TcState* s, long long B);
+int tc_reserve(TcState* s, long long B) { return ensure_act(s, B); }
 static int ensure_act(TcState* s, long long B) {
     const long long P = (B + 127) / 128 * 128;
     if (P <= s->cap) return 0;
@@ -524,6 +599,8 @@ static int launch_gemm(TcState* s, const float* a_hi, const float* a_lo, long lo
 }
 
 int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
+    if (a.input_kind != IN_QUAT && (a.steps != 1 || a.do_step || a.pose_out != nullptr))
+        return tc_fail(s, "tensor-core path: axis-angle input is the prior mode (one evaluation, no step)");
     if (ensure_act(s, a.B)) return 1;
     const long long P = (a.B + 127) / 128 * 128;
     const pndf_config& cfg = s->cfg;
@@ -549,6 +626,8 @@ int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
         EncParams ep{};
         ep.pose = pose_cur; ep.encw = a.encw; ep.z0_hi = zhi(0); ep.z0_lo = zlo(0); ep.B = a.B; ep.z0_ld = zw[0];
         ep.normalise = a.normalise; ep.use_enc = cfg.use_enc; ep.enc_act = cfg.enc_act; ep.enc_beta = cfg.enc_beta;
+        ep.input_kind = a.input_kind;
+        if (a.dn != nullptr) ep.dn = *a.dn;
         ep.feat_out = a.want_grad ? featp : nullptr;
         if (esoft) tc_enc_kernel<true, false><<<tiles32, 256, enc_sm_total<false>(), st>>>(ep);
         else tc_enc_kernel<false, false><<<tiles32, 256, enc_sm_total<false>(), st>>>(ep);
@@ -597,6 +676,7 @@ int tc_run(TcState* s, const TcArgs& a, cudaStream_t st, int64_t* launches) {
         rp.pose_out = a.do_step ? a.pose_out : nullptr;
         if (last && a.do_step) { rp.n_peers = a.n_peers; for (int r = 0; r < a.n_peers; ++r) rp.peer_pose[r] = a.peer_pose[r]; }
         rp.feat = featp; rp.feat_out = nullptr; rp.pose = pose_cur;
+        rp.dn = DenoiseFuse{};      // the update was applied by the forward kernel
         if (esoft) tc_enc_kernel<true, true><<<tiles32, 256, enc_sm_total<true>(), st>>>(rp);
         else tc_enc_kernel<false, true><<<tiles32, 256, enc_sm_total<true>(), st>>>(rp);
         if (tc_check(s, "tc_enc_kernel (reverse) launch")) return 1;
