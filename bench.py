@@ -239,7 +239,10 @@ def run_other_configs(eng, dev, rank, world, gather):
     ms = _max_over_ranks(a.elapsed_time(b), dev, world)
     out["C4_denoise_100_adam_steps"] = {"sequences_per_gpu": S, "frames": T, "steps": 100, "ms": ms,
                                         "kernel_launches_per_gpu": int(eng.launch_count() - l0), "graph_launches_per_gpu": 1,
-                                        "note": "two sequence groups = two parallel launch chains inside ONE CUDA graph",
+                                        "note": ("tensor-core engine: ONE chain of 15 kernels per Adam step (the update of step t-1 in the "
+                                                 "prologue of the first one) + the last update, replayed as ONE CUDA graph"
+                                                 if eng.tile_for_batch(S * T) == 128 else
+                                                 "two sequence groups = two parallel launch chains inside ONE CUDA graph"),
                                         "pose_steps_per_s": world * S * T * 100 / ms * 1e3, "sequences_per_s": world * S / ms * 1e3}
     del aa, aa0
 
@@ -452,7 +455,7 @@ def main():
                           "algorithmic_flops_per_pose": FLOPS_PER_PROJECTION} if tc else None),
             "roofline_fp32_path": {"bound": "fp32_fma", "achieved": ach_tf, "peak": p_nominal, "unit": "TFLOP/s", "frac": ach_tf / p_nominal,
                          "traffic": traffic, "kernel": "pndf_fused_kernel<1> (the fused fp32-FMA kernel, tile policy 32; what runs for "
-                                                        "axis-angle / training / small batches)", "kernel_ms": ffma_ms,
+                                                        "training / small batches)", "kernel_ms": ffma_ms,
                          "peak_source": "nominal fp32 FMA: %d SMs x 128 lanes x 2 x %.0f MHz (tensor cores unused: fp32 parity bar 1e-5)"
                                         % (eng.num_sms(), sm_max),
                          "peak_measured_ffma2": p_ffma2, "frac_of_measured": ach_tf / max(p_ffma, p_ffma2),

@@ -271,10 +271,10 @@ int pndf_knn_exact(int device, const float* query_dev, int64_t Q, const float* d
 /* Tile size / arithmetic engine of the forward / forward+reverse launches.  By default every launch picks it from ITS batch size:
  *   B <= 8 x SMs (1 184 on a B200): the fused FFMA kernel's 8-pose small-tile variant (2.4x lower latency than 32-pose tiles at the
  *     reference's real call sites, B = 10 in experiments/sample_poses.py:96);
- *   larger plain quaternion batches: the tensor-core engine ("tile 128": DFNet GEMMs as 3xTF32 tcgen05 kernels on 128-pose
- *     tiles, pndf_tc.cu);
- *   axis-angle input, training exports, tangent launches: the fused FFMA kernel with 32-pose tiles (8-pose tiles while one round
- *     of them covers the batch).
+ *   larger batches, quaternion input or the axis-angle prior mode (pndf_prior_grad, pndf_denoise_prior): the tensor-core engine
+ *     ("tile 128": DFNet GEMMs as 3xTF32 tcgen05 kernels on 128-pose tiles, pndf_tc.cu);
+ *   training exports, tangent launches, prior-mode batches above 131 072 poses: the fused FFMA kernel with 32-pose tiles (8-pose
+ *     tiles while one round of them covers the batch).
  * The engines differ in fp32 summation order / split arithmetic (same parity bars), so a caller that splits ONE batch over several
  * launches or GPUs and wants bits identical to the unsplit run pins the tile the whole batch would get:
  * tile = pndf_tile_for_batch(h, B_total), pndf_set_tile_policy(h, tile), launches, pndf_set_tile_policy(h, 0).

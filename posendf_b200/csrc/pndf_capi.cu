@@ -339,9 +339,9 @@ bool use_small_tile(const pndf_handle* h, const KParams& p, int mode) {
     if (h->tile_policy != 0) return h->tile_policy == 8;
     return small_tile_for(h, p.B);
 }
-// Large batches of plain quaternion poses (forward, forward + gradient, projection steps) take the tensor-core path: the DFNet
-// GEMMs as 3xTF32 tcgen05 kernels, ~2x the FFMA kernel.  Everything else (axis-angle prior / denoise loop, training
-// exports, debug dump, small batches) stays on the fused FFMA kernel.
+// Batches beyond one round of 8-pose tiles (forward, forward + gradient, projection steps on quaternions; the axis-angle prior and
+// the denoise loop) take the tensor-core engine: the DFNet GEMMs as 3xTF32 tcgen05 kernels, ~3x the FFMA kernel.
+// Training exports, tangent launches, the debug dump and small batches stay on the fused FFMA kernel.
 // the engine a plain launch over B poses gets (environment override, pinned policy, batch size)
 bool tc_for_batch(const pndf_handle* h, long long B) {
     if (!h->tc) return false;
