@@ -805,7 +805,9 @@ int pndf_denoise_prior(pndf_handle* h, float* aa_dev, int64_t S, int64_t T, int 
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     CUDA_OK(cudaStreamIsCapturing(st, &cs));
     bool graphed = false;
-    if (cs == cudaStreamCaptureStatusNone && !getenv("PNDF_NO_GRAPH")) {
+    // (the tensor-core chain is 15 kernels of ~0.1 ms per step: the host stays far ahead of the GPU with plain launches, while
+    //  capturing + instantiating a 1 501-node graph costs tens of milliseconds per call)
+    if (cs == cudaStreamCaptureStatusNone && !getenv("PNDF_NO_GRAPH") && !on_tc) {
         // capture on an internal stream (the caller's may be the legacy default stream, which cannot be captured), replay on the caller's
         if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) h->cap_stream = nullptr;
         if (h->cap_stream && cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
