@@ -278,6 +278,35 @@ def test_large_batch_properties():
     assert torch.equal(y, x - d.reshape(-1, 1, 1) * g)
 
 
+def test_tensor_core_passes_of_a_very_large_batch(tile_size):
+    """the tensor-core engine walks batches above 131 072 poses in passes (its activations live in HBM between the layer kernels):
+    a 2-step projection over 131 072 + 333 poses equals the same call on the two parts, bit for bit, and follows the fp64 oracle"""
+    if tile_size not in ("auto", "128"):
+        pytest.skip("one pass structure per engine: the fused kernel has none")
+    meta, _ = load_golden("lrelu_enc_s1")
+    cfg = case_cfg(meta)
+    params, _ = case_inputs(meta)
+    eng = make_engine(meta, params)
+    B = 131072 + 333
+    poses = synth.make_poses(77, B)
+    x = torch.from_numpy(poses).cuda()
+    y = x.clone()
+    d = eng.project_(y, steps=2)
+    parts = []
+    eng.set_tile_policy(eng.tile_for_batch(B))
+    for lo, hi in ((0, 131072), (131072, B)):
+        z = x[lo:hi].clone()
+        dz = eng.project_(z, steps=2)
+        parts.append((z, dz))
+    eng.set_tile_policy(0)
+    torch.cuda.synchronize()
+    assert torch.equal(y, torch.cat([p[0] for p in parts])) and torch.equal(d, torch.cat([p[1] for p in parts]))
+    idx = np.unique(np.concatenate([np.linspace(0, B - 1, 192).astype(np.int64), np.arange(131072 - 8, 131072 + 8), np.arange(B - 8, B)]))
+    p64 = {k: v.astype(np.float64) for k, v in params.items()}
+    xref, _ = onp.project(p64, poses[idx].astype(np.float64), cfg, steps=2)
+    assert_pose_parity(y.cpu().numpy()[idx], xref)
+
+
 # ---------------------------------------------------------------------------- reference call surface on the GPU
 def _opt(meta):
     cfg = case_cfg(meta)
