@@ -247,11 +247,13 @@ def test_prior_term_axis_angle(name):
     assert_grad_parity(g.cpu().numpy(), gref, tol=2e-5)
 
 
-def test_host_buffer_projection_matches_device_projection():
+@pytest.mark.parametrize("B", [148 * 4 * 32 + 1234, 70000 + 77])
+def test_host_buffer_projection_matches_device_projection(B):
+    """pndf_project_host (pinned host buffers, chunked upload / compute / download overlap; head / body / tail chunk schedule on the
+    tensor-core engine) == pndf_project on the same batch, bit for bit"""
     meta, _ = load_golden("lrelu_enc_s1")
     params, _ = case_inputs(meta)
     eng = make_engine(meta, params)
-    B = 148 * 4 * 32 + 1234
     poses = torch.from_numpy(synth.make_poses(8, B)).pin_memory()
     out, dist = eng.project_host(poses, steps=2)
     x = poses.cuda().contiguous()
