@@ -139,7 +139,11 @@ int pndf_prior_grad(pndf_handle* h, const float* aa_dev, int64_t B, const float*
  * back from the previous launch's distances); a small per-sequence kernel applies the last update.  Sequences are independent,
  * so they run as two groups with their own launch chains side by side (the tail round of one group's launch overlaps the other
  * group's next launch).  The 2 x (steps_total + 1) launches are captured into a CUDA graph and replayed as one graph launch on
- * `stream` (PNDF_NO_GRAPH=1 in the environment: plain launches on `stream` and one internal stream).  The SMPL temporal / data terms need licensed SMPL files and are out of scope. */
+ * `stream` (PNDF_NO_GRAPH=1 in the environment: plain launches on `stream` and one internal stream).  When S*T poses select the
+ * tensor-core engine (more than 8 x SMs poses, at most 131 072) the loop is ONE chain over all sequences instead -- 15 kernels per
+ * step, the pending Adam update in the prologue of the first one -- issued as plain launches on `stream` (the host stays ahead of
+ * them; a 1 501-node graph would cost more to build than it saves).  Same results within the parity bars, same arguments.
+ * The SMPL temporal / data terms need licensed SMPL files and are out of scope. */
 int pndf_denoise_prior(pndf_handle* h, float* aa_dev, int64_t S, int64_t T, int iterations, int steps_per_iter, float lr,
                        float* dist_dev, float* loss_hist_dev, void* stream);
 
